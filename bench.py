@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- RealNVP rows/sec on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N ...            # reference CPU path (oracle port)
+
+Workload (default ``c3``, BASELINE.json configs[2], the configuration the metric's "fit ... at
+1/2/4/8 B200" is quoted on): RealNVP fit on synthetic N(0,1) rows, D=32, Cd=8, 16 coupling
+layers, hidden (128,), tanh, fp32.  A *step* is one optimisation step of the hot path over one
+batch: fused forward+backward launch, gradient all-reduce (N>1), fused Adam launch
+(reference realnvp.py:246-251).  Weak scaling: 65,536 rows per GPU per step.
+
+value      rows/s, whole job, inputs resident in HBM (a different random batch of a resident
+           data set larger than L2 every step -- no L2 flush needed).
+e2e        same metric through the public API ``RealNVP.fit(X, C)`` with pinned HOST arrays:
+           H2D of every step's rows and D2H of the losses inside the timed region.
+roofline   dominant kernel (fused fwd+bwd): algorithmic mask-aware GEMM flops per launch
+           (909,312 / row for c3) / its mean duration from CUDA events inside the
+           timed region, against the FP32-FMA peak 2*128*SMs*max clock (the binding pipe; the
+           path is compute-bound, HBM fraction is reported beside it).
+cpu_baseline  the oracle port (same ATen ops as the reference) timed on the host cores on a
+           bounded sample, rank 0, N=1 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (D, Cd, L, hidden, rows per GPU per step, description)
+    "c2": (2, 1, 8, (10,), 1 << 20, "configs[1]: 2-D moons flow, 1-D condition, L=8, H=10"),
+    "c3": (32, 8, 16, (128,), 65536, "configs[2]: fit, 32-D rows, 8-D condition, L=16, H=128"),
+    "c4": (64, 16, 24, (128,), 32768, "configs[3]: 64-D rows, 16-D condition, L=24, H=128 (H assumed)"),
+    "c5": (128, 32, 8, (512,), 16384, "configs[4]: 128-D rows, 32-D condition, L=8 (assumed), H=512"),
+}
+
+
+def flops_per_row(D, Cd, L, H):
+    """Mask-aware GEMM flops per row, 2 per MAC."""
+    fwd = bwd = 0
+    for i in range(L):
+        nT = (D - (i & 1) + 1) // 2
+        nK = D - nT
+        fwd += 4 * H * (nK + Cd + nT)
+        bwd += 2 * (2 * H * 2 * nT + 2 * H * (nK + Cd) + (2 * H * nK if i > 0 else 0))
+    return fwd, fwd + bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_step_rate(D, Cd, L, hidden, rows, reps, warm):
+    """The oracle port (ATen CPU ops, all host threads): full optimisation steps -> rows/s."""
+    import torch
+    from oracle import realnvp_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.init_params(D, Cd, L, hidden, seed=0)
+    st = O.AdamState(params, lr=1e-4)
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(rows, D, generator=g)
+    C = torch.randn(rows, Cd, generator=g) if Cd else None
+    times = []
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        _, grads = O.loss_and_grads(X, C, params, L, len(hidden), "tanh")
+        O.adam_step(params, grads, st)
+        dt = time.perf_counter() - t0
+        if it >= warm:
+            times.append(dt)
+    return rows * len(times) / sum(times), torch.get_num_threads(), sum(times) / len(times)
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
+    pure Python/torch and cannot travel to the GPU box; the port issues the same ATen calls)."""
+    D, Cd, L, hidden, per_gpu, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = 16384
+    rate, cores, step_s = cpu_port_step_rate(D, Cd, L, hidden, rows, reps=args.steps, warm=args.warmup)
+    line = {
+        "impl": "reference", "metric": "RealNVP fit rows/sec (fwd+bwd+Adam)", "value": rate, "unit": "rows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + " -- " + desc, "rows_per_step": rows,
+                   "note": "reference CPU path = oracle port (same ATen ops), bounded sample"},
+        "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} optimisation steps of {rows} rows"},
+        "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows-per-gpu", type=int, default=0, help="rows per GPU per step (default per workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from probaforms_b200.models import RealNVP, RealNVPLayer, NormalizingFlow
+
+    D, Cd, L, hidden, per_gpu, desc = wl
+    if args.rows_per_gpu:
+        per_gpu = args.rows_per_gpu
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- flow with random-init weights of the named architecture (identical on every rank)
+    torch.manual_seed(0)
+    layers = [RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, hidden, "tanh") for i in range(L)]
+    nf = NormalizingFlow(layers, prior=None).to(dev)
+    eng = nf._fused()
+
+    # ---- resident synthetic data set, larger than L2 (126 MB): random rows gathered every step
+    n_res = max(4 * per_gpu, (768 << 20) // (4 * (D + Cd)))
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    X = torch.randn(n_res, D, device=dev, generator=gen)
+    C = torch.randn(n_res, Cd, device=dev, generator=gen) if Cd else None
+    perm = torch.randint(0, n_res, ((K + W) * per_gpu,), device=dev, generator=gen)
+    losses = torch.zeros(K + W, device=dev)
+    n_global = per_gpu * world
+    lr, wd = 1e-4, 0.0
+
+    def step(s):
+        eng.fit_step(X, C, perm[s * per_gpu:(s + 1) * per_gpu], per_gpu, n_global, lr, wd,
+                     losses[s:s + 1], world=world)
+
+    eng.zero_grads()
+    for s in range(W):
+        step(s)
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, barrier + sync on both sides, CUDA events, max over ranks
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = eng.launches
+    ev0.record()
+    for s in range(K):
+        a, b = kev[s]
+        a.record()
+        eng.backward(X, C, perm[(W + s) * per_gpu:(W + s + 1) * per_gpu], per_gpu, -1.0 / n_global)
+        b.record()
+        if world > 1:
+            dist.all_reduce(eng._gbuf)
+        eng.adam_step(lr, wd, loss_dst=losses[W + s:W + s + 1], loss_scale=-1.0 / n_global)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launches - launches0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in kev) / K], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(ms)
+    rows_per_s = n_global * K / (total_ms * 1e-3)
+    final_loss = float(losses[W + K - 1])
+
+    # ---- end to end through the public API with pinned host arrays
+    e2e = None
+    if not args.no_e2e:
+        model = RealNVP(n_layers=L, hidden=hidden, activation="tanh", batch_size=n_global, n_epochs=1, lr=lr)
+        n_e2e = n_global * max(4, min(K, 16))
+        hgen = torch.Generator().manual_seed(7)                      # same host data on every rank
+        Xh = torch.randn(n_e2e, D, generator=hgen).pin_memory()
+        Ch = torch.randn(n_e2e, Cd, generator=hgen).pin_memory() if Cd else None
+        torch.manual_seed(0)
+        model.fit(Xh[: 2 * n_global], None if Ch is None else Ch[: 2 * n_global])      # warm-up: init + first launches
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.fit(Xh, Ch)                                           # H2D of all rows, steps, D2H of the losses
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        steps_e2e = n_e2e // n_global
+        e2e = {"value": n_e2e / float(dt), "unit": "rows/s",
+               "h2d_bytes_per_step": n_global * 4 * (D + Cd) + 8 * n_global, "d2h_bytes_per_step": 4,
+               "steps": steps_e2e, "api": "RealNVP.fit(X_host, C_host), n_epochs=1, replicated data-parallel"}
+
+    if rank == 0:
+        H = hidden[0]
+        f_fwd, f_fit = flops_per_row(D, Cd, L, H)
+        kms = float(kern_ms)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        fp32_peak = 2 * 128 * sms * sm_max * 1e6 / 1e12                   # TFLOP/s, FFMA pipe
+        achieved = per_gpu * f_fit / (kms * 1e-3) / 1e12
+        bytes_row = 4 * (D + Cd) + 8
+        line = {
+            "metric": "RealNVP fit rows/sec (fwd+bwd+Adam)", "value": rows_per_s, "unit": "rows/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload + " -- " + desc, "D": D, "Cd": Cd, "n_layers": L,
+                       "hidden": list(hidden), "activation": "tanh", "rows_per_gpu_per_step": per_gpu,
+                       "global_batch": n_global, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": f"inputs larger than L2: each step gathers a fresh random batch from a resident "
+                             f"{n_res * 4 * (D + Cd) >> 20} MiB data set",
+                       "final_loss": final_loss},
+            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak, "traffic": None,
+                         "kernel": "rnvp_tile_kernel<TR,2> (fused forward+backward)", "kernel_ms": kms,
+                         "kernel_share_of_step": kms / (total_ms / K),
+                         "flops_per_row": f_fit, "rows_per_launch": per_gpu,
+                         "peak_source": f"2*128 lanes*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
+                                        "tensor/HBM peaks do not bind this FP32-FMA kernel",
+                         "hbm_gbs": per_gpu * bytes_row / (kms * 1e-3) / 1e9,
+                         "hbm_frac_of_measured": per_gpu * bytes_row / (kms * 1e-3) / 1e9 / hbm_peak},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            rows = 16384
+            rate, cores, step_s = cpu_port_step_rate(D, Cd, L, hidden, rows, reps=3, warm=1)
+            line["cpu_baseline"] = {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port",
+                                    "sample": f"3 optimisation steps of {rows} rows ({step_s:.2f} s each), oracle port"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+/* rnvp.h -- C ABI of the B200-native RealNVP hot path (librnvp_b200.so).
+ *
+ * Drop-in boundary for hse-cs/probaforms' RealNVP path.  The reference has no
+ * native code: its hot path is Python calling torch eager ops.  Each entry
+ * point below replaces the reference interface cited next to it (paths are
+ * relative to the reference repo root); INTEGRATION.md shows the ctypes stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain C types only; every pointer named d_* is a DEVICE pointer to
+ *    contiguous fp32 (or int64 where stated) memory owned by the caller (torch);
+ *    the library never allocates or frees caller-visible memory.  The opaque
+ *    descriptor owns a few KB of device tables (its per-tile op programs).
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no
+ *    entry point synchronises, so calls are CUDA-graph capturable.
+ *  - every function returns 0 on success, a negative RNVP_E* code for argument /
+ *    planning errors, or a positive cudaError_t.  rnvp_last_error() returns a
+ *    thread-local message.  Nothing throws, exits, or falls back to the CPU.
+ *  - parameters cross the boundary in the reference's own layout: one flat fp32
+ *    buffer in `nf.parameters()` order, per coupling layer i
+ *    nn_t.0.weight [h0, D+Cd], nn_t.0.bias [h0], ..., nn_t.{2n}.weight [D, h_last],
+ *    nn_t.{2n}.bias [D], then the same for nn_s  (probaforms/models/realnvp.py:69-70,
+ *    gen_network realnvp.py:19-43).  rnvp_pack_params() converts it to the
+ *    kernel-private mask-compacted "packed" layout; gradients come back through
+ *    rnvp_unpack_grads() with exact zeros on masked rows/columns, as autograd
+ *    produces them in the reference.
+ */
+#ifndef RNVP_H
+#define RNVP_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rnvp_desc rnvp_desc;
+
+enum {
+  RNVP_OK = 0,
+  RNVP_EINVAL = -1,      /* bad argument */
+  RNVP_ESHAPE = -2,      /* flow shape cannot be planned (e.g. shared-memory budget) */
+  RNVP_ENODEVICE = -3,   /* no sm_100 device / wrong architecture */
+  RNVP_EALLOC = -4
+};
+enum { RNVP_ACT_TANH = 1, RNVP_ACT_RELU = 2 };   /* realnvp.py:32-37 */
+
+/* Build the descriptor of a flow on the CURRENT CUDA device.
+ * Replaces RealNVP._model_init's layer construction (realnvp.py:195-204):
+ * L coupling layers over var_size=D, cond_size=Cd (0 when C is None), conditioner
+ * hidden widths hidden[0..n_hidden-1], mask_i[j] = (j+i)%2 (realnvp.py:199). */
+int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int act, rnvp_desc** out);
+void rnvp_desc_destroy(rnvp_desc* d);
+
+/* sizes, in floats */
+int64_t rnvp_param_count(const rnvp_desc* d);    /* P: flat reference-layout parameters */
+int64_t rnvp_packed_count(const rnvp_desc* d);   /* kernel-private packed layout */
+/* bytes of scratch rnvp_backward needs (x_T stash; stays L2 resident) */
+int64_t rnvp_workspace_bytes(const rnvp_desc* d);
+/* offsets[2*k], offsets[2*k+1] = (float offset, numel) of the k-th tensor of nf.parameters();
+ * n = 4*(n_hidden+1)*L entries pairs.  Returns the number of tensors. */
+int rnvp_param_tensors(const rnvp_desc* d, int64_t* offsets, int max_tensors);
+/* rows per CTA tile chosen for mode 0/1/2, and CTAs launched for N rows (introspection / bench) */
+int rnvp_plan_info(const rnvp_desc* d, int mode, int* tile_rows, int* smem_bytes, int* n_ops, int* kernel_family);
+
+/* flat (reference layout) -> packed; run after every parameter update */
+int rnvp_pack_params(const rnvp_desc* d, const float* d_flat, float* d_packed, void* stream);
+/* packed gradient accumulator -> flat reference layout (masked entries written as exact 0) */
+int rnvp_unpack_grads(const rnvp_desc* d, const float* d_gpacked, float* d_gflat, void* stream);
+
+/* Forward pass = body of NormalizingFlow.log_prob before the mean (nflow.py:107-115) over
+ * layers [layer_begin, layer_end): z, per-row sum of log|det J|, and
+ * logp = logdet + MultivariateNormal(0,I).log_prob(z).  Any of d_z/d_logdet/d_logp may be NULL.
+ * layer_end - layer_begin == 1 is RealNVPLayer.f (realnvp.py:73-101).  d_C NULL iff Cd == 0.
+ * d_idx (int64[N], may be NULL) gathers rows: row r reads X[idx[r]], C[idx[r]]. */
+int rnvp_forward(const rnvp_desc* d, const float* d_packed, const float* d_X, const float* d_C,
+                 const int64_t* d_idx, int64_t N, int layer_begin, int layer_end,
+                 float* d_z, float* d_logdet, float* d_logp, void* stream);
+
+/* Inverse pass = NormalizingFlow.sample after the prior draw (nflow.py:142-143): layers
+ * [layer_begin, layer_end) applied in REVERSE order to the latent rows d_Y (the prior sample);
+ * one layer is RealNVPLayer.g (realnvp.py:104-129). */
+int rnvp_inverse(const rnvp_desc* d, const float* d_packed, const float* d_Y, const float* d_C,
+                 int64_t N, int layer_begin, int layer_end, float* d_X, void* stream);
+
+/* Fused forward + backward of  out = scale * sum_rows logp(row)  (loss.backward() of
+ * loss = -nf.log_prob(X, C), realnvp.py:246-250, is scale = -1/N).  Activations are recomputed,
+ * weight gradients are ACCUMULATED into d_gpacked (caller zeroes it), sum_rows logp is
+ * accumulated into d_logp_sum (1 float, may be NULL), per-row logp optionally written. */
+int rnvp_backward(const rnvp_desc* d, const float* d_packed, const float* d_X, const float* d_C,
+                  const int64_t* d_idx, int64_t N, float scale, float* d_gpacked, float* d_logp_sum,
+                  float* d_logp, void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* torch.optim.Adam step (realnvp.py:205-207, 251; betas/eps as constructed there) on the flat
+ * parameters, refreshing d_packed in the same pass.  The gradient is read from the packed
+ * accumulator d_gpacked, or, when d_gflat_in is non-NULL, from a reference-layout gradient (the
+ * .grad tensors autograd filled); grad_scale multiplies it first (e.g. 1/world_size after an
+ * all-reduce).  step is the 1-based step count; scalar hyper-parameters are doubles because torch
+ * does the bias-correction arithmetic in Python doubles.  d_gflat_out (may be NULL) receives the
+ * reference-layout gradient.  zero_gpacked != 0 re-zeroes the accumulator entries it consumed
+ * (opt.zero_grad(), realnvp.py:249).  If d_loss_src is non-NULL, *d_loss_dst = *d_loss_src *
+ * loss_scale (loss_history entry, realnvp.py:254) and *d_loss_src is re-zeroed with the gradients. */
+int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_gpacked,
+                   const float* d_gflat_in, float* d_exp_avg, float* d_exp_avg_sq, float* d_gflat_out,
+                   float grad_scale, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, int zero_gpacked, float* d_loss_src,
+                   float* d_loss_dst, float loss_scale, void* stream);
+
+const char* rnvp_last_error(void);
+int rnvp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNVP_H */

@@ -1,0 +1,359 @@
+// Host side of librnvp_b200.so: flow descriptor, packed-layout maps, per-tile program planner,
+// pack / unpack / fused-Adam kernels and the extern "C" entry points declared in include/rnvp.h.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/rnvp.h"
+#include "rnvp_plan.h"
+#include "rnvp_planner.h"
+
+cudaError_t rnvp_launch_tile(int mode, int TR, const RnvpKArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
+int rnvp_tile_occupancy(int mode, int TR, size_t smem_bytes);
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+
+struct Program {
+  RnvpOp* d_ops = nullptr;
+  RnvpChunk* d_chunks = nullptr;
+  int n_ops = 0, n_chunks = 0;
+  RnvpSmem sm{};
+  int TR = 0;
+  size_t smem_bytes = 0;
+  int stash_per_cta = 0;
+  int occupancy = 1;
+};
+
+}  // namespace
+
+struct rnvp_desc : rnvp_planner::FlowGeom {
+  int device = 0, num_sms = 1;
+  int* d_p2f = nullptr;   // packed index -> flat index or -1
+  int* d_f2p = nullptr;   // flat index -> packed index or -1
+  std::map<std::tuple<int, int, int>, Program> programs;
+  std::mutex mu;
+};
+
+namespace {
+using namespace rnvp_planner;
+
+int get_program(rnvp_desc* d, int mode, int l0, int l1, Program** out) {
+  std::lock_guard<std::mutex> lock(d->mu);
+  auto key = std::make_tuple(mode, l0, l1);
+  auto it = d->programs.find(key);
+  if (it != d->programs.end()) { *out = &it->second; return 0; }
+  Builder b;
+  b.d = d; b.mode = mode; b.l0 = l0; b.l1 = l1;
+  const bool ok = b.plan_best();
+  if (!ok) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "flow does not fit the shared-memory plan (D=%d Cd=%d H0=%d mode=%d needs %d B > %d B)",
+             d->D, d->Cd, d->hidden[0], mode, b.sm.total_floats * 4, d->max_smem);
+    return fail(RNVP_ESHAPE, msg);
+  }
+  b.build();
+  Program p;
+  p.n_ops = (int)b.ops.size();
+  p.n_chunks = (int)b.chunks.size();
+  p.sm = b.sm;
+  p.TR = b.TR;
+  p.smem_bytes = (size_t)b.sm.total_floats * 4;
+  p.stash_per_cta = b.stash_per_cta;
+  cudaError_t e = cudaMalloc(&p.d_ops, sizeof(RnvpOp) * std::max(p.n_ops, 1));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ops)");
+  e = cudaMalloc(&p.d_chunks, sizeof(RnvpChunk) * std::max(p.n_chunks, 1));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(chunks)");
+  e = cudaMemcpy(p.d_ops, b.ops.data(), sizeof(RnvpOp) * p.n_ops, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(ops)");
+  if (p.n_chunks) {
+    e = cudaMemcpy(p.d_chunks, b.chunks.data(), sizeof(RnvpChunk) * p.n_chunks, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(chunks)");
+  }
+  p.occupancy = std::max(1, rnvp_tile_occupancy(mode, p.TR, p.smem_bytes));
+  auto ins = d->programs.emplace(key, p);
+  *out = &ins.first->second;
+  return 0;
+}
+
+// ------------------------------------------------------- small utility kernels
+__global__ void pack_kernel(const float* __restrict__ flat, float* __restrict__ packed,
+                            const int* __restrict__ p2f, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int f = p2f[i];
+    packed[i] = f >= 0 ? flat[f] : 0.0f;
+  }
+}
+__global__ void unpack_kernel(const float* __restrict__ gpacked, float* __restrict__ gflat,
+                              const int* __restrict__ f2p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int p = f2p[i];
+    gflat[i] = p >= 0 ? gpacked[p] : 0.0f;
+  }
+}
+// torch.optim.Adam single-tensor update (torch/optim/adam.py _single_tensor_adam), fused with the
+// gradient gather from the packed accumulator (or a reference-layout gradient), the refresh of the
+// packed parameter copy, the re-zeroing of the accumulator and the hand-off of the step's loss.
+__global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packed, float* __restrict__ gpacked,
+                            const float* __restrict__ gflat_in, float* __restrict__ m, float* __restrict__ v,
+                            float* __restrict__ gflat_out, const int* __restrict__ f2p, int n, float grad_scale,
+                            float wd, float one_minus_b1, float b2, float one_minus_b2, float step_size,
+                            float bc2_sqrt, float eps, int zero_gpacked, float* loss_src, float* loss_dst,
+                            float loss_scale) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && loss_src) {
+    if (loss_dst) *loss_dst = *loss_src * loss_scale;
+    if (zero_gpacked) *loss_src = 0.0f;
+  }
+  if (i >= n) return;
+  const int p = f2p[i];
+  float g;
+  if (gflat_in) g = gflat_in[i] * grad_scale;
+  else {
+    g = p >= 0 ? gpacked[p] * grad_scale : 0.0f;
+    if (zero_gpacked && p >= 0) gpacked[p] = 0.0f;
+  }
+  if (gflat_out) gflat_out[i] = g;
+  float th = theta[i];
+  if (wd != 0.0f) g = fmaf(wd, th, g);                 // grad.add(param, alpha=weight_decay)
+  float mi = m[i], vi = v[i];
+  mi = fmaf(one_minus_b1, g - mi, mi);                 // exp_avg.lerp_(grad, 1-beta1)
+  vi = fmaf(one_minus_b2 * g, g, vi * b2);             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  const float denom = __fsqrt_rn(vi) / bc2_sqrt + eps; // (sqrt(v)/sqrt(bc2)).add_(eps)
+  th = fmaf(-step_size, mi / denom, th);               // param.addcdiv_(exp_avg, denom, value=-step_size)
+  m[i] = mi; v[i] = vi; theta[i] = th;
+  if (p >= 0) packed[p] = th;
+}
+
+int check_desc(const rnvp_desc* d) { return d ? 0 : fail(RNVP_EINVAL, "null descriptor"); }
+
+int run_tile(rnvp_desc* d, int mode, int l0, int l1, RnvpKArgs& a, void* workspace, int64_t workspace_bytes,
+             cudaStream_t stream) {
+  if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
+  if (a.N <= 0) return 0;
+  Program* p = nullptr;
+  int rc = get_program(d, mode, l0, l1, &p);
+  if (rc) return rc;
+  const int R = 8 * p->TR;
+  const long long n_tiles = (a.N + R - 1) / R;
+  if (n_tiles > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
+  int grid = (int)std::min<long long>(n_tiles, (long long)d->num_sms * p->occupancy);
+  if (mode == 2) {
+    const long long per_cta = (long long)p->stash_per_cta * 4;
+    const long long fit = per_cta > 0 ? workspace_bytes / per_cta : grid;
+    if (!workspace || fit < 1) return fail(RNVP_EINVAL, "rnvp_backward: workspace too small (see rnvp_workspace_bytes)");
+    grid = (int)std::min<long long>(grid, fit);
+    a.stash = (float*)workspace;
+    a.stash_per_cta = p->stash_per_cta;
+  }
+  a.ops = p->d_ops;
+  a.chunks = p->d_chunks;
+  a.n_ops = p->n_ops;
+  a.n_chunks = p->n_chunks;
+  a.n_tiles = (int)n_tiles;
+  a.D = d->D;
+  a.Cd = d->Cd;
+  a.sm = p->sm;
+  cudaError_t e = rnvp_launch_tile(mode, p->TR, a, grid, p->smem_bytes, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "tile kernel launch");
+  return 0;
+}
+
+}  // namespace
+
+// ===================================================================== C ABI
+extern "C" {
+
+int rnvp_version(void) { return 100; }
+const char* rnvp_last_error(void) { return g_err.c_str(); }
+
+int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int act, rnvp_desc** out) {
+  if (!out) return fail(RNVP_EINVAL, "out is null");
+  *out = nullptr;
+  if (D < 1 || Cd < 0 || L < 1 || n_hidden < 1 || n_hidden > RNVP_MAX_HIDDEN || !hidden)
+    return fail(RNVP_EINVAL, "bad flow shape");
+  if (act != RNVP_ACT_TANH && act != RNVP_ACT_RELU) return fail(RNVP_EINVAL, "act must be RNVP_ACT_TANH or RNVP_ACT_RELU");
+  for (int q = 0; q < n_hidden; ++q)
+    if (hidden[q] < 1) return fail(RNVP_EINVAL, "hidden width must be >= 1");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "librnvp_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    return fail(RNVP_ENODEVICE, msg);
+  }
+  rnvp_desc* d = new rnvp_desc();
+  d->D = D; d->Cd = Cd; d->L = L; d->nh = n_hidden; d->act = act;
+  for (int q = 0; q < n_hidden; ++q) d->hidden[q] = hidden[q];
+  d->device = dev;
+  d->num_sms = prop.multiProcessorCount;
+  d->max_smem = (int)prop.sharedMemPerBlockOptin;
+  build_layout(d);
+  if (d->P >= 0x7fffffffLL) { delete d; return fail(RNVP_ESHAPE, "flow too large (>= 2^31 parameters)"); }
+  std::vector<int> p2f, f2p;
+  build_maps(d, p2f, f2p);
+  e = cudaMalloc(&d->d_p2f, sizeof(int) * p2f.size());
+  if (e == cudaSuccess) e = cudaMalloc(&d->d_f2p, sizeof(int) * std::max<size_t>(f2p.size(), 1));
+  if (e == cudaSuccess) e = cudaMemcpy(d->d_p2f, p2f.data(), sizeof(int) * p2f.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d->d_f2p, f2p.data(), sizeof(int) * f2p.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
+  *out = d;
+  return 0;
+}
+
+void rnvp_desc_destroy(rnvp_desc* d) {
+  if (!d) return;
+  for (auto& kv : d->programs) {
+    cudaFree(kv.second.d_ops);
+    cudaFree(kv.second.d_chunks);
+  }
+  cudaFree(d->d_p2f);
+  cudaFree(d->d_f2p);
+  delete d;
+}
+
+int64_t rnvp_param_count(const rnvp_desc* d) { return d ? d->P : -1; }
+int64_t rnvp_packed_count(const rnvp_desc* d) { return d ? d->packed : -1; }
+
+int64_t rnvp_workspace_bytes(const rnvp_desc* dc) {
+  rnvp_desc* d = const_cast<rnvp_desc*>(dc);
+  if (!d) return -1;
+  Program* p = nullptr;
+  if (get_program(d, 2, 0, d->L, &p)) return -1;
+  return (int64_t)p->stash_per_cta * 4 * d->num_sms * p->occupancy;
+}
+
+int rnvp_param_tensors(const rnvp_desc* d, int64_t* offsets, int max_tensors) {
+  if (check_desc(d)) return RNVP_EINVAL;
+  int k = 0;
+  for (int i = 0; i < d->L; ++i)
+    for (int net = 0; net < 2; ++net)
+      for (int q = 0; q <= d->nh; ++q) {
+        const LinearGeom& g = d->layers[i].lin[q];
+        if (offsets && k + 2 <= max_tensors) {
+          offsets[2 * k] = g.flat_w[net]; offsets[2 * k + 1] = (int64_t)g.in_full * g.out_full;
+          offsets[2 * k + 2] = g.flat_b[net]; offsets[2 * k + 3] = g.out_full;
+        }
+        k += 2;
+      }
+  return k;
+}
+
+int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_bytes, int* n_ops, int* kernel_family) {
+  rnvp_desc* d = const_cast<rnvp_desc*>(dc);
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (mode < 0 || mode > 2) return fail(RNVP_EINVAL, "mode must be 0, 1 or 2");
+  Program* p = nullptr;
+  int rc = get_program(d, mode, 0, d->L, &p);
+  if (rc) return rc;
+  if (tile_rows) *tile_rows = 8 * p->TR;
+  if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
+  if (n_ops) *n_ops = p->n_ops;
+  if (kernel_family) *kernel_family = 0;
+  return 0;
+}
+
+int rnvp_pack_params(const rnvp_desc* d, const float* d_flat, float* d_packed, void* stream) {
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (!d_flat || !d_packed) return fail(RNVP_EINVAL, "null buffer");
+  const int n = (int)d->packed;
+  pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_flat, d_packed, d->d_p2f, n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "pack_kernel");
+}
+
+int rnvp_unpack_grads(const rnvp_desc* d, const float* d_gpacked, float* d_gflat, void* stream) {
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (!d_gpacked || !d_gflat) return fail(RNVP_EINVAL, "null buffer");
+  const int n = (int)d->P;
+  unpack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_gpacked, d_gflat, d->d_f2p, n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "unpack_kernel");
+}
+
+int rnvp_forward(const rnvp_desc* dc, const float* d_packed, const float* d_X, const float* d_C,
+                 const int64_t* d_idx, int64_t N, int layer_begin, int layer_end, float* d_z, float* d_logdet,
+                 float* d_logp, void* stream) {
+  rnvp_desc* d = const_cast<rnvp_desc*>(dc);
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (N < 0 || !d_packed || (N > 0 && !d_X)) return fail(RNVP_EINVAL, "rnvp_forward: null buffer");
+  if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_forward: C must be given iff cond_size > 0");
+  RnvpKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = d_packed; a.X = d_X; a.C = d_C; a.idx = (const long long*)d_idx; a.N = N;
+  a.out_x = d_z; a.out_logdet = d_logdet; a.out_logp = d_logp;
+  return run_tile(d, 0, layer_begin, layer_end, a, nullptr, 0, (cudaStream_t)stream);
+}
+
+int rnvp_inverse(const rnvp_desc* dc, const float* d_packed, const float* d_Y, const float* d_C, int64_t N,
+                 int layer_begin, int layer_end, float* d_X, void* stream) {
+  rnvp_desc* d = const_cast<rnvp_desc*>(dc);
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (N < 0 || !d_packed || (N > 0 && (!d_Y || !d_X))) return fail(RNVP_EINVAL, "rnvp_inverse: null buffer");
+  if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_inverse: C must be given iff cond_size > 0");
+  RnvpKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = d_packed; a.X = d_Y; a.C = d_C; a.N = N; a.out_x = d_X;
+  return run_tile(d, 1, layer_begin, layer_end, a, nullptr, 0, (cudaStream_t)stream);
+}
+
+int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, const float* d_C,
+                  const int64_t* d_idx, int64_t N, float scale, float* d_gpacked, float* d_logp_sum, float* d_logp,
+                  void* d_workspace, int64_t workspace_bytes, void* stream) {
+  rnvp_desc* d = const_cast<rnvp_desc*>(dc);
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (N < 0 || !d_packed || !d_gpacked || (N > 0 && !d_X)) return fail(RNVP_EINVAL, "rnvp_backward: null buffer");
+  if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_backward: C must be given iff cond_size > 0");
+  RnvpKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = d_packed; a.X = d_X; a.C = d_C; a.idx = (const long long*)d_idx; a.N = N;
+  a.out_logp = d_logp; a.gpacked = d_gpacked; a.loss_sum = d_logp_sum; a.scale = scale;
+  return run_tile(d, 2, 0, d->L, a, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_gpacked, const float* d_gflat_in,
+                   float* d_exp_avg, float* d_exp_avg_sq, float* d_gflat_out, float grad_scale, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int64_t step, int zero_gpacked,
+                   float* d_loss_src, float* d_loss_dst, float loss_scale, void* stream) {
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (!d_flat || !d_packed || (!d_gpacked && !d_gflat_in) || !d_exp_avg || !d_exp_avg_sq)
+    return fail(RNVP_EINVAL, "rnvp_adam_step: null buffer");
+  if (step < 1) return fail(RNVP_EINVAL, "rnvp_adam_step: step is 1-based");
+  // scalar step math in double, as torch does on the host
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const int n = (int)d->P;
+  adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      d_flat, d_packed, d_gpacked, d_gflat_in, d_exp_avg, d_exp_avg_sq, d_gflat_out, d->d_f2p, n, grad_scale,
+      (float)weight_decay, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt, (float)eps,
+      zero_gpacked, d_loss_src, d_loss_dst, loss_scale);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "adam_kernel");
+}
+
+}  // extern "C"
