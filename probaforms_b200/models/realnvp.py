@@ -220,7 +220,9 @@ class RealNVP(GenModel):
         A = np.asarray(A)
         if A.dtype != np.float32:
             A = A.astype(np.float32)
-        return torch.from_numpy(np.ascontiguousarray(A)).to(dev)
+        if A.ndim > 0:                                   # (ascontiguousarray would promote a 0-d value to 1-d)
+            A = np.ascontiguousarray(A)
+        return torch.from_numpy(A).to(dev)
 
     @staticmethod
     def _epoch_permutation(n):
