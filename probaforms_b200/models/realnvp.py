@@ -21,6 +21,7 @@ import torch.nn as nn
 from .interfaces import GenModel
 from .nflow import InvertibleLayer, NormalizingFlow
 from ..engine import FlowEngine
+from ..batching import epoch_permutation, batch_bounds, shard_bounds
 
 
 def _default_device():
@@ -224,17 +225,6 @@ class RealNVP(GenModel):
             A = np.ascontiguousarray(A)
         return torch.from_numpy(A).to(dev)
 
-    @staticmethod
-    def _epoch_permutation(n):
-        """Row order of one epoch, consuming the global torch RNG exactly as the reference's fresh
-        ``DataLoader(dataset, batch_size, shuffle=True)`` does (realnvp.py:237): one int64 draw for
-        the loader's base seed, one for the RandomSampler seed, then randperm(n) from that seed."""
-        torch.empty((), dtype=torch.int64).random_()
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())
-        g = torch.Generator()
-        g.manual_seed(seed)
-        return torch.randperm(n, generator=g)
-
     # ------------------------------------------------------------------ fit
     def fit(self, X, C=None):
         """Fit on X [n, var_size] (numpy), optional conditions C [n, cond_size] (realnvp.py:210-262).
@@ -268,19 +258,12 @@ class RealNVP(GenModel):
             epochs = bar
         eng.zero_grads()
         for _ in epochs:
-            perm = self._epoch_permutation(n)
-            if world > 1:                                   # identical order on every rank
-                perm = perm.to(dev)
-                dist.broadcast(perm, src=0)
-            else:
-                perm = perm.to(dev, non_blocking=True)
-            n_steps = (n + bs - 1) // bs
-            losses = torch.empty(n_steps, dtype=torch.float32, device=dev)
-            for s in range(n_steps):
-                b0 = s * bs
-                nb = min(bs, n - b0)                        # last partial batch is kept (drop_last=False)
-                lo = b0 + (nb * rank) // world
-                hi = b0 + (nb * (rank + 1)) // world
+            # identical order on every rank: the sampler seed of rank 0 is broadcast
+            perm = epoch_permutation(n, device=dev if world > 1 else None).to(dev, non_blocking=True)
+            bounds = batch_bounds(n, bs)
+            losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
+            for s, (b0, nb) in enumerate(bounds):           # last partial batch is kept (drop_last=False)
+                lo, hi = shard_bounds(b0, nb, rank, world)
                 eng.fit_step(Xd, Cd, perm[lo:hi], hi - lo, nb, self.lr, self.weight_decay,
                              losses[s:s + 1], world=world)
             host = losses.cpu()                             # the epoch's only device->host sync
