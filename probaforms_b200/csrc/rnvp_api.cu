@@ -15,9 +15,13 @@
 #include "../../include/rnvp.h"
 #include "rnvp_plan.h"
 #include "rnvp_planner.h"
+#include "rnvp_small.h"
 
 cudaError_t rnvp_launch_tile(int mode, int TR, const RnvpKArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
 int rnvp_tile_occupancy(int mode, int TR, size_t smem_bytes);
+cudaError_t rnvp_launch_small(int NE, int NC, int act, int mode, const RnvpSmallArgs& a, int grid, size_t smem,
+                              cudaStream_t st);
+int rnvp_small_rows_per_block();
 
 namespace {
 
@@ -48,6 +52,7 @@ struct rnvp_desc : rnvp_planner::FlowGeom {
   int device = 0, num_sms = 1;
   int* d_p2f = nullptr;   // packed index -> flat index or -1
   int* d_f2p = nullptr;   // flat index -> packed index or -1
+  int* d_f2p2 = nullptr;  // flat index -> index in the small-flow layout or -1 (nullptr if unused)
   std::map<std::tuple<int, int, int>, Program> programs;
   std::mutex mu;
 };
@@ -115,7 +120,8 @@ __global__ void unpack_kernel(const float* __restrict__ gpacked, float* __restri
 // packed parameter copy, the re-zeroing of the accumulator and the hand-off of the step's loss.
 __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packed, float* __restrict__ gpacked,
                             const float* __restrict__ gflat_in, float* __restrict__ m, float* __restrict__ v,
-                            float* __restrict__ gflat_out, const int* __restrict__ f2p, int n, float grad_scale,
+                            float* __restrict__ gflat_out, const int* __restrict__ f2p, const int* __restrict__ f2p2, int n,
+                            float grad_scale,
                             float wd, float one_minus_b1, float b2, float one_minus_b2, float step_size,
                             float bc2_sqrt, float eps, int zero_gpacked, float* loss_src, float* loss_dst,
                             float loss_scale) {
@@ -142,6 +148,10 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packe
   th = fmaf(-step_size, mi / denom, th);               // param.addcdiv_(exp_avg, denom, value=-step_size)
   m[i] = mi; v[i] = vi; theta[i] = th;
   if (p >= 0) packed[p] = th;
+  if (f2p2) {
+    const int p2 = f2p2[i];
+    if (p2 >= 0) packed[p2] = th;
+  }
 }
 
 int check_desc(const rnvp_desc* d) { return d ? 0 : fail(RNVP_EINVAL, "null descriptor"); }
@@ -175,6 +185,24 @@ int run_tile(rnvp_desc* d, int mode, int l0, int l1, RnvpKArgs& a, void* workspa
   a.sm = p->sm;
   cudaError_t e = rnvp_launch_tile(mode, p->TR, a, grid, p->smem_bytes, stream);
   if (e != cudaSuccess) return cuda_fail(e, "tile kernel launch");
+  return 0;
+}
+
+int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
+              const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream) {
+  if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
+  if (N <= 0) return 0;
+  RnvpSmallArgs a;
+  a.packed_small = packed + d->small_off;
+  a.X = X; a.C = C; a.idx = idx; a.N = N;
+  a.out_x = out_x; a.out_logdet = out_logdet; a.out_logp = out_logp;
+  a.D = d->D; a.Cd = d->Cd; a.H = d->hidden[0]; a.rec = d->srec; a.small_floats = d->small_floats;
+  a.l0 = l0; a.l1 = l1;
+  const long long rpb = rnvp_small_rows_per_block();
+  const long long blocks = (N + rpb - 1) / rpb;
+  const int grid = (int)std::min<long long>(blocks, (long long)d->num_sms * 8);
+  cudaError_t e = rnvp_launch_small(d->sNE, d->sNC, d->act, mode, a, grid, (size_t)d->small_floats * 4, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "small-flow kernel launch");
   return 0;
 }
 
@@ -213,8 +241,14 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
   d->max_smem = (int)prop.sharedMemPerBlockOptin;
   build_layout(d);
   if (d->P >= 0x7fffffffLL) { delete d; return fail(RNVP_ESHAPE, "flow too large (>= 2^31 parameters)"); }
-  std::vector<int> p2f, f2p;
+  std::vector<int> p2f, f2p, f2p2;
   build_maps(d, p2f, f2p);
+  build_small_map(d, p2f, f2p2);
+  if (d->small_ok) {
+    e = cudaMalloc(&d->d_f2p2, sizeof(int) * f2p2.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_f2p2, f2p2.data(), sizeof(int) * f2p2.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
+  }
   e = cudaMalloc(&d->d_p2f, sizeof(int) * p2f.size());
   if (e == cudaSuccess) e = cudaMalloc(&d->d_f2p, sizeof(int) * std::max<size_t>(f2p.size(), 1));
   if (e == cudaSuccess) e = cudaMemcpy(d->d_p2f, p2f.data(), sizeof(int) * p2f.size(), cudaMemcpyHostToDevice);
@@ -232,6 +266,7 @@ void rnvp_desc_destroy(rnvp_desc* d) {
   }
   cudaFree(d->d_p2f);
   cudaFree(d->d_f2p);
+  cudaFree(d->d_f2p2);
   delete d;
 }
 
@@ -272,7 +307,7 @@ int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_byte
   if (tile_rows) *tile_rows = 8 * p->TR;
   if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
   if (n_ops) *n_ops = p->n_ops;
-  if (kernel_family) *kernel_family = 0;
+  if (kernel_family) *kernel_family = (mode != 2 && d->small_ok) ? 1 : 0;
   return 0;
 }
 
@@ -301,6 +336,9 @@ int rnvp_forward(const rnvp_desc* dc, const float* d_packed, const float* d_X, c
   if (check_desc(d)) return RNVP_EINVAL;
   if (N < 0 || !d_packed || (N > 0 && !d_X)) return fail(RNVP_EINVAL, "rnvp_forward: null buffer");
   if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_forward: C must be given iff cond_size > 0");
+  if (d->small_ok)
+    return run_small(d, 0, layer_begin, layer_end, d_packed, d_X, d_C, (const long long*)d_idx, N, d_z, d_logdet,
+                     d_logp, (cudaStream_t)stream);
   RnvpKArgs a;
   memset(&a, 0, sizeof(a));
   a.packed = d_packed; a.X = d_X; a.C = d_C; a.idx = (const long long*)d_idx; a.N = N;
@@ -314,6 +352,9 @@ int rnvp_inverse(const rnvp_desc* dc, const float* d_packed, const float* d_Y, c
   if (check_desc(d)) return RNVP_EINVAL;
   if (N < 0 || !d_packed || (N > 0 && (!d_Y || !d_X))) return fail(RNVP_EINVAL, "rnvp_inverse: null buffer");
   if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_inverse: C must be given iff cond_size > 0");
+  if (d->small_ok)
+    return run_small(d, 1, layer_begin, layer_end, d_packed, d_Y, d_C, nullptr, N, d_X, nullptr, nullptr,
+                     (cudaStream_t)stream);
   RnvpKArgs a;
   memset(&a, 0, sizeof(a));
   a.packed = d_packed; a.X = d_Y; a.C = d_C; a.N = N; a.out_x = d_X;
@@ -349,7 +390,8 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
   const float bc2_sqrt = (float)sqrt(bc2);
   const int n = (int)d->P;
   adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      d_flat, d_packed, d_gpacked, d_gflat_in, d_exp_avg, d_exp_avg_sq, d_gflat_out, d->d_f2p, n, grad_scale,
+      d_flat, d_packed, d_gpacked, d_gflat_in, d_exp_avg, d_exp_avg_sq, d_gflat_out, d->d_f2p, d->d_f2p2, n,
+      grad_scale,
       (float)weight_decay, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt, (float)eps,
       zero_gpacked, d_loss_src, d_loss_dst, loss_scale);
   cudaError_t e = cudaGetLastError();

@@ -41,7 +41,12 @@ struct FlowGeom {
   int hidden[RNVP_MAX_HIDDEN];
   int max_smem = 232448;     // bytes of opt-in dynamic shared memory per CTA (sm_100: 227 KB)
   std::vector<LayerGeom> layers;
-  int64_t P = 0, packed = 0;
+  int64_t P = 0, packed = 0;     // packed = tile layout + (optional) small-flow layout
+  int64_t packed_tile = 0;       // floats of the tile-kernel layout (the gradient accumulator covers only this)
+  // row-per-thread small-flow layout (rnvp_small.cu): one hidden layer, ceil(D/2) <= 4, Cd <= 4
+  bool small_ok = false;
+  int sNE = 0, sNC = 0, srec = 0, snet = 0, small_floats = 0;
+  int64_t small_off = 0;
 };
 
 // ------------------------------------------------------------------ layout
@@ -79,7 +84,55 @@ inline void build_layout(FlowGeom* d) {
     }
   }
   d->P = flat;
-  d->packed = std::max(packed, 4);
+  d->packed_tile = std::max(packed, 4);
+  d->packed = d->packed_tile;
+  // small-flow layout
+  const int ne = (D + 1) / 2;
+  d->small_ok = false;
+  if (nh == 1 && ne <= 4 && Cd <= 4) {
+    d->sNE = ne <= 1 ? 1 : (ne <= 2 ? 2 : 4);
+    d->sNC = Cd == 0 ? 0 : (Cd <= 1 ? 1 : (Cd <= 2 ? 2 : 4));
+    d->srec = ceil4(2 * d->sNE + d->sNC + 1);
+    d->snet = d->hidden[0] * d->srec + ceil4(d->sNE);
+    const int64_t total = (int64_t)d->L * 2 * d->snet;
+    if (total * 4 <= 64 * 1024) {
+      d->small_ok = true;
+      d->small_floats = (int)total;
+      d->small_off = d->packed_tile;
+      d->packed = d->small_off + total;
+    }
+  }
+}
+
+// second flat -> packed map: position of each parameter in the small-flow layout (or -1)
+inline void build_small_map(const FlowGeom* d, std::vector<int>& p2f, std::vector<int>& f2p2) {
+  f2p2.assign(d->P, -1);
+  if (!d->small_ok) return;
+  const int D = d->D, Cd = d->Cd, H = d->hidden[0], NE = d->sNE, NC = d->sNC, rec = d->srec;
+  for (int i = 0; i < d->L; ++i) {
+    const LayerGeom& lg = d->layers[i];
+    const LinearGeom& g0 = lg.lin[0];
+    const LinearGeom& g1 = lg.lin[1];
+    for (int net = 0; net < 2; ++net) {
+      const int64_t base = d->small_off + ((int64_t)i * 2 + net) * d->snet;
+      auto put = [&](int64_t p, int64_t f) { p2f[p] = (int)f; f2p2[f] = (int)p; };
+      for (int j = 0; j < H; ++j) {
+        const int64_t u = base + (int64_t)j * rec;
+        for (int e = 0; e < NE; ++e) {
+          const int fk = lg.par == 0 ? 2 * e + 1 : 2 * e;            // conditioning (keep) feature
+          if (fk < D) put(u + e, g0.flat_w[net] + (int64_t)j * (D + Cd) + fk);
+          const int ft = lg.par == 0 ? 2 * e : 2 * e + 1;            // transformed feature
+          if (ft < D) put(u + NE + NC + 1 + e, g1.flat_w[net] + (int64_t)ft * H + j);
+        }
+        for (int k = 0; k < NC && k < Cd; ++k) put(u + NE + k, g0.flat_w[net] + (int64_t)j * (D + Cd) + D + k);
+        put(u + NE + NC, g0.flat_b[net] + j);
+      }
+      for (int e = 0; e < NE; ++e) {
+        const int ft = lg.par == 0 ? 2 * e : 2 * e + 1;
+        if (ft < D) put(base + (int64_t)H * rec + e, g1.flat_b[net] + ft);
+      }
+    }
+  }
 }
 
 inline void build_maps(const FlowGeom* d, std::vector<int>& p2f, std::vector<int>& f2p) {

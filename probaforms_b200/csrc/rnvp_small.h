@@ -1,0 +1,16 @@
+// Arguments of the row-per-thread small-flow kernels (rnvp_small.cu).
+#pragma once
+#include <stdint.h>
+
+struct RnvpSmallArgs {
+  const float* packed_small;   // per layer, per net: H records [w1_x NE | w1_c NC | b1 | w2 NE] (padded to rec), then b2
+  const float* X;              // rows (forward) or latent noise (inverse), [N][D]
+  const float* C;              // [N][Cd] or nullptr
+  const long long* idx;        // optional row gather
+  long long N;
+  float* out_x;                // z / x, may be nullptr in forward mode
+  float* out_logdet;
+  float* out_logp;
+  int D, Cd, H, rec, small_floats;
+  int l0, l1;
+};
