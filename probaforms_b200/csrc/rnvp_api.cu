@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <map>
@@ -67,7 +68,8 @@ int get_program(rnvp_desc* d, int mode, int l0, int l1, Program** out) {
   if (it != d->programs.end()) { *out = &it->second; return 0; }
   Builder b;
   b.d = d; b.mode = mode; b.l0 = l0; b.l1 = l1;
-  const bool ok = b.plan_best();
+  const char* force = getenv("RNVP_FORCE_TR");     // development knob: force the row-tile size
+  const bool ok = b.plan_best(force ? atoi(force) : 0);
   if (!ok) {
     char msg[256];
     snprintf(msg, sizeof(msg), "flow does not fit the shared-memory plan (D=%d Cd=%d H0=%d mode=%d needs %d B > %d B)",
