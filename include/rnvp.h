@@ -105,6 +105,10 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
                    double weight_decay, int64_t step, int zero_gpacked, float* d_loss_src,
                    float* d_loss_dst, float loss_scale, void* stream);
 
+/* Tensor-core primitive self-test (tcgen05.mma kind::tf32, A in TMEM, B in shared memory):
+ * D[128,N] = A[128,K] * B[N,K]^T on device buffers; passes = 1 (plain TF32) or 3 (split, fp32-grade). */
+int rnvp_mma_selftest(const float* d_A, const float* d_B, float* d_D, int N, int K, int passes, void* stream);
+
 const char* rnvp_last_error(void);
 int rnvp_version(void);
 

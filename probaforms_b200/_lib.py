@@ -41,6 +41,7 @@ SIGNATURES = {
     "rnvp_adam_step": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p,
                                  C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.c_int64, C.c_int, c_f32_p, c_f32_p, C.c_float, c_stream]),
+    "rnvp_mma_selftest": (C.c_int, [c_f32_p, c_f32_p, c_f32_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "rnvp_last_error": (C.c_char_p, []),
     "rnvp_version": (C.c_int, []),
 }

@@ -23,6 +23,7 @@ int rnvp_tile_occupancy(int mode, int TR, size_t smem_bytes);
 cudaError_t rnvp_launch_small(int NE, int NC, int act, int mode, const RnvpSmallArgs& a, int grid, size_t smem,
                               cudaStream_t st);
 int rnvp_small_rows_per_block();
+cudaError_t rnvp_launch_mma_selftest(const float* A, const float* B, float* D, int N, int K, int passes, cudaStream_t st);
 
 namespace {
 
@@ -398,6 +399,14 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
       zero_gpacked, d_loss_src, d_loss_dst, loss_scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "adam_kernel");
+}
+
+int rnvp_mma_selftest(const float* d_A, const float* d_B, float* d_D, int N, int K, int passes, void* stream) {
+  if (!d_A || !d_B || !d_D) return fail(RNVP_EINVAL, "rnvp_mma_selftest: null buffer");
+  if (N < 16 || N > 256 || N % 16 || K < 8 || K > 64 || K % 8 || (passes != 1 && passes != 3))
+    return fail(RNVP_EINVAL, "rnvp_mma_selftest: need N%16==0 in [16,256], K%8==0 in [8,64], passes 1 or 3");
+  cudaError_t e = rnvp_launch_mma_selftest(d_A, d_B, d_D, N, K, passes, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "mma_selftest_kernel");
 }
 
 }  // extern "C"
