@@ -53,7 +53,8 @@ void rnvp_desc_destroy(rnvp_desc* d);
 
 /* sizes, in floats */
 int64_t rnvp_param_count(const rnvp_desc* d);    /* P: flat reference-layout parameters */
-int64_t rnvp_packed_count(const rnvp_desc* d);   /* kernel-private packed layout */
+int64_t rnvp_packed_count(const rnvp_desc* d);   /* kernel-private packed layouts (all kernel families) */
+int64_t rnvp_grad_count(const rnvp_desc* d);     /* floats of the packed gradient accumulator d_gpacked */
 /* bytes of scratch rnvp_backward needs (x_T stash; stays L2 resident) */
 int64_t rnvp_workspace_bytes(const rnvp_desc* d);
 /* offsets[2*k], offsets[2*k+1] = (float offset, numel) of the k-th tensor of nf.parameters();
@@ -104,6 +105,11 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
                    float grad_scale, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, int zero_gpacked, float* d_loss_src,
                    float* d_loss_dst, float loss_scale, void* stream);
+
+/* Kernel-family selection for rnvp_forward / rnvp_inverse: 0 = auto (tcgen05 TF32x3 kernels where the shape is
+ * eligible -- one hidden layer, D/2 in {16,32} --, else the small-flow or FP32 tile kernels), 1 = FP32-FMA kernels
+ * only, 2 = same as auto.  rnvp_plan_info reports the family chosen (0 tile, 1 small-flow, 2 tcgen05). */
+int rnvp_set_path(rnvp_desc* d, int path);
 
 /* Tensor-core primitive self-test (tcgen05.mma kind::tf32, A in TMEM, B in shared memory):
  * D[128,N] = A[128,K] * B[N,K]^T on device buffers; passes = 1 (plain TF32) or 3 (split, fp32-grade). */

@@ -26,6 +26,7 @@ SIGNATURES = {
     "rnvp_desc_destroy": (None, [c_desc_p]),
     "rnvp_param_count": (C.c_int64, [c_desc_p]),
     "rnvp_packed_count": (C.c_int64, [c_desc_p]),
+    "rnvp_grad_count": (C.c_int64, [c_desc_p]),
     "rnvp_workspace_bytes": (C.c_int64, [c_desc_p]),
     "rnvp_param_tensors": (C.c_int, [c_desc_p, C.POINTER(C.c_int64), C.c_int]),
     "rnvp_plan_info": (C.c_int, [c_desc_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "rnvp_adam_step": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p,
                                  C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.c_int64, C.c_int, c_f32_p, c_f32_p, C.c_float, c_stream]),
+    "rnvp_set_path": (C.c_int, [c_desc_p, C.c_int]),
     "rnvp_mma_selftest": (C.c_int, [c_f32_p, c_f32_p, c_f32_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "rnvp_last_error": (C.c_char_p, []),
     "rnvp_version": (C.c_int, []),

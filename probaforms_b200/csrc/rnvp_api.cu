@@ -17,12 +17,15 @@
 #include "rnvp_plan.h"
 #include "rnvp_planner.h"
 #include "rnvp_small.h"
+#include "rnvp_mma.h"
 
 cudaError_t rnvp_launch_tile(int mode, int TR, const RnvpKArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
 int rnvp_tile_occupancy(int mode, int TR, size_t smem_bytes);
 cudaError_t rnvp_launch_small(int NE, int NC, int act, int mode, const RnvpSmallArgs& a, int grid, size_t smem,
                               cudaStream_t st);
 int rnvp_small_rows_per_block();
+cudaError_t rnvp_launch_mma(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st);
+size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats);
 cudaError_t rnvp_launch_mma_selftest(const float* A, const float* B, float* D, int N, int K, int passes, cudaStream_t st);
 
 namespace {
@@ -55,6 +58,8 @@ struct rnvp_desc : rnvp_planner::FlowGeom {
   int* d_p2f = nullptr;   // packed index -> flat index or -1
   int* d_f2p = nullptr;   // flat index -> packed index or -1
   int* d_f2p2 = nullptr;  // flat index -> index in the small-flow layout or -1 (nullptr if unused)
+  int* d_m2f = nullptr;   // tcgen05 region: 4*flat + code (0 hi, 1 lo, 2 full) or -1
+  int path = 0;           // 0 auto, 1 FP32 tile/small kernels only, 2 tcgen05 where eligible
   std::map<std::tuple<int, int, int>, Program> programs;
   std::mutex mu;
 };
@@ -108,6 +113,24 @@ __global__ void pack_kernel(const float* __restrict__ flat, float* __restrict__ 
   if (i < n) {
     int f = p2f[i];
     packed[i] = f >= 0 ? flat[f] : 0.0f;
+  }
+}
+// tcgen05 weight images: TF32 round-to-nearest "hi" part, fp32 remainder "lo", or the plain value
+__global__ void pack_mma_kernel(const float* __restrict__ flat, float* __restrict__ img, const int* __restrict__ m2f, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int m = m2f[i];
+    float out = 0.0f;
+    if (m >= 0) {
+      const float v = flat[m >> 2];
+      uint32_t h;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+      const int code = m & 3;
+      uint32_t l;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));
+      out = code == 0 ? __uint_as_float(h) : (code == 1 ? __uint_as_float(l) : v);
+    }
+    img[i] = out;
   }
 }
 __global__ void unpack_kernel(const float* __restrict__ gpacked, float* __restrict__ gflat,
@@ -209,6 +232,27 @@ int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const
   return 0;
 }
 
+bool use_mma(const rnvp_desc* d) { return d->mma_ok && d->path != 1; }
+
+int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
+            const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream) {
+  if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
+  if (N <= 0) return 0;
+  RnvpMmaArgs a;
+  a.wimg = packed + d->mma_off;
+  a.X = X; a.C = C; a.idx = idx; a.N = N;
+  a.out_x = out_x; a.out_logdet = out_logdet; a.out_logp = out_logp;
+  a.Cd = d->Cd; a.H = d->hidden[0]; a.l0 = l0; a.l1 = l1;
+  a.layer_floats = d->m_layer_floats; a.w1_floats = d->m_w1_floats; a.w2_floats = d->m_w2_floats;
+  const long long pairs = (N + 255) / 256;
+  if (pairs > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
+  a.n_pairs = (int)pairs;
+  const int grid = (int)std::min<long long>(pairs, d->num_sms);
+  cudaError_t e = rnvp_launch_mma(d->mDH, d->act, mode, a, grid, rnvp_mma_smem_bytes(d->m_w1_floats, d->m_w2_floats), stream);
+  if (e != cudaSuccess) return cuda_fail(e, "tcgen05 kernel launch");
+  return 0;
+}
+
 }  // namespace
 
 // ===================================================================== C ABI
@@ -252,6 +296,13 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
     if (e == cudaSuccess) e = cudaMemcpy(d->d_f2p2, f2p2.data(), sizeof(int) * f2p2.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
   }
+  if (d->mma_ok) {
+    std::vector<int> m2f;
+    build_mma_map(d, m2f);
+    e = cudaMalloc(&d->d_m2f, sizeof(int) * m2f.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_m2f, m2f.data(), sizeof(int) * m2f.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
+  }
   e = cudaMalloc(&d->d_p2f, sizeof(int) * p2f.size());
   if (e == cudaSuccess) e = cudaMalloc(&d->d_f2p, sizeof(int) * std::max<size_t>(f2p.size(), 1));
   if (e == cudaSuccess) e = cudaMemcpy(d->d_p2f, p2f.data(), sizeof(int) * p2f.size(), cudaMemcpyHostToDevice);
@@ -270,11 +321,13 @@ void rnvp_desc_destroy(rnvp_desc* d) {
   cudaFree(d->d_p2f);
   cudaFree(d->d_f2p);
   cudaFree(d->d_f2p2);
+  cudaFree(d->d_m2f);
   delete d;
 }
 
 int64_t rnvp_param_count(const rnvp_desc* d) { return d ? d->P : -1; }
 int64_t rnvp_packed_count(const rnvp_desc* d) { return d ? d->packed : -1; }
+int64_t rnvp_grad_count(const rnvp_desc* d) { return d ? d->packed_tile : -1; }
 
 int64_t rnvp_workspace_bytes(const rnvp_desc* dc) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
@@ -310,16 +363,21 @@ int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_byte
   if (tile_rows) *tile_rows = 8 * p->TR;
   if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
   if (n_ops) *n_ops = p->n_ops;
-  if (kernel_family) *kernel_family = (mode != 2 && d->small_ok) ? 1 : 0;
+  if (kernel_family) *kernel_family = mode == 2 ? 0 : (use_mma(d) ? 2 : (d->small_ok ? 1 : 0));
   return 0;
 }
 
 int rnvp_pack_params(const rnvp_desc* d, const float* d_flat, float* d_packed, void* stream) {
   if (check_desc(d)) return RNVP_EINVAL;
   if (!d_flat || !d_packed) return fail(RNVP_EINVAL, "null buffer");
-  const int n = (int)d->packed;
+  const int n = (int)d->packed_gather;
   pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_flat, d_packed, d->d_p2f, n);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && d->mma_ok) {
+    const long long m = d->mma_floats;
+    pack_mma_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_flat, d_packed + d->mma_off, d->d_m2f, m);
+    e = cudaGetLastError();
+  }
   return e == cudaSuccess ? 0 : cuda_fail(e, "pack_kernel");
 }
 
@@ -339,6 +397,9 @@ int rnvp_forward(const rnvp_desc* dc, const float* d_packed, const float* d_X, c
   if (check_desc(d)) return RNVP_EINVAL;
   if (N < 0 || !d_packed || (N > 0 && !d_X)) return fail(RNVP_EINVAL, "rnvp_forward: null buffer");
   if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_forward: C must be given iff cond_size > 0");
+  if (use_mma(d))
+    return run_mma(d, 0, layer_begin, layer_end, d_packed, d_X, d_C, (const long long*)d_idx, N, d_z, d_logdet, d_logp,
+                   (cudaStream_t)stream);
   if (d->small_ok)
     return run_small(d, 0, layer_begin, layer_end, d_packed, d_X, d_C, (const long long*)d_idx, N, d_z, d_logdet,
                      d_logp, (cudaStream_t)stream);
@@ -355,6 +416,8 @@ int rnvp_inverse(const rnvp_desc* dc, const float* d_packed, const float* d_Y, c
   if (check_desc(d)) return RNVP_EINVAL;
   if (N < 0 || !d_packed || (N > 0 && (!d_Y || !d_X))) return fail(RNVP_EINVAL, "rnvp_inverse: null buffer");
   if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_inverse: C must be given iff cond_size > 0");
+  if (use_mma(d))
+    return run_mma(d, 1, layer_begin, layer_end, d_packed, d_Y, d_C, nullptr, N, d_X, nullptr, nullptr, (cudaStream_t)stream);
   if (d->small_ok)
     return run_small(d, 1, layer_begin, layer_end, d_packed, d_Y, d_C, nullptr, N, d_X, nullptr, nullptr,
                      (cudaStream_t)stream);
@@ -399,6 +462,13 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
       zero_gpacked, d_loss_src, d_loss_dst, loss_scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "adam_kernel");
+}
+
+int rnvp_set_path(rnvp_desc* d, int path) {
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (path < 0 || path > 2) return fail(RNVP_EINVAL, "path must be 0 (auto), 1 (fp32 kernels) or 2 (tcgen05 where eligible)");
+  d->path = path;
+  return 0;
 }
 
 int rnvp_mma_selftest(const float* d_A, const float* d_B, float* d_D, int N, int K, int passes, void* stream) {

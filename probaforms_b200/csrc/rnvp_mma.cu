@@ -1,6 +1,21 @@
-// tcgen05 (5th-gen tensor core) path of the RealNVP hot path -- work in progress.
+// tcgen05 (5th-gen tensor core) path of the RealNVP hot path: fused forward (log-density) and inverse
+// (sampling) passes for flows whose conditioner GEMMs are real contractions (hidden width >= 32,
+// D/2 in {16, 32}: BASELINE configs c3, c4).
 //
-// This file currently holds the primitive self-test: D[128 x N] = A[128 x K] * B[N x K]^T with A
+// rnvp_mma_kernel -- one persistent CTA per SM, 10 warps, processes PAIRS of 128-row tiles:
+//   warp 0      TMA producer: per coupling layer one bulk copy of the W1 image and one of the W2 image
+//               (TF32 hi/lo splits, pre-tiled in the no-swizzle K-major core-matrix layout) into smem
+//   warp 1      MMA issuer (one thread): tcgen05.mma kind::tf32, A operands in TMEM, accumulators in TMEM,
+//               error-compensated 3-pass split (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) = fp32-grade accuracy
+//   warps 2-5   epilogue group of tile 0, warps 6-9 of tile 1: ONE THREAD PER ROW.  The row (x, c, log-det)
+//               lives in registers for the whole flow; per layer the thread writes u=[x_K,c,1] to TMEM,
+//               turns each GEMM1 accumulator chunk into tanh(.) hi/lo in place (tcgen05.ld/st), and applies
+//               the coupling y_T = x_T*exp(s)+t from the GEMM2 accumulators.
+//   The two tiles ping-pong: while one tile's threads run the tanh epilogue (MUFU-bound), the tensor core
+//   runs the other tile's MMAs.  Hidden units are processed in chunks of CU per net so that a tile needs
+//   <= 256 TMEM columns (u_hi, u_lo, D1/A_hi, A_lo, D2).  b1 rides in GEMM1 as an extra K column of ones.
+//
+// Also here: the primitive self-test: D[128 x N] = A[128 x K] * B[N x K]^T with A
 // staged in TMEM (tcgen05.st, one thread per row), B in shared memory in the no-swizzle K-major
 // core-matrix layout, kind::tf32 MMAs issued by one thread, completion through tcgen05.commit on an
 // mbarrier, and the accumulator read back with tcgen05.ld.  passes = 1: plain TF32;
@@ -9,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tc05.cuh"
+#include "rnvp_mma.h"
 
 namespace {
 using namespace tc05;
@@ -85,7 +101,363 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+// ============================================================ fused forward / inverse kernel
+constexpr int MMA_THREADS = 320;
+
+template <int ACT>
+__device__ __forceinline__ float act_mma(float v) {
+  if (ACT == 1) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+  }
+  return fmaxf(v, 0.0f);
+}
+
+enum { B_W1F = 0, B_W1E, B_W2F, B_W2E, B_UF0, B_UF1, B_D1F0, B_D1F1, B_AF0, B_AF1, B_D2F0, B_D2F1, B_COUNT };
+
+template <int DH, int CDMAX, int CU, bool NETSEQ, int ACT, int MODE>
+__global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_constant__ RnvpMmaArgs a) {
+  constexpr int K1PMAX = (DH + CDMAX + 1 + 7) & ~7;
+  constexpr int NTP = (DH + 15) & ~15;
+  // NETSEQ: the chunks of nn_t are processed before those of nn_s (t is parked in registers meanwhile), which halves
+  // the accumulator columns so that D=64 flows also get the separate correction accumulator C2
+  constexpr int D1W = NETSEQ ? CU : 2 * CU;          // columns of one GEMM1 accumulator chunk
+  constexpr int D2W = NETSEQ ? NTP : 2 * NTP;        // columns of the GEMM2 accumulator(s) alive at a time
+  constexpr int U_HI = 0, U_LO = K1PMAX, D1C = 2 * K1PMAX, A_LO = D1C + D1W, D2C = A_LO + D1W;
+  // The tensor core accumulates in fp32 with TRUNCATION (measured: -0.3 ulp bias per accumulation, see
+  // tools/mma_rounding_probe.py), so the tiny TF32-split correction products are kept out of the long main chains:
+  // in GEMM1 they are issued first (while the accumulator is still tiny), in GEMM2 they get their own accumulator C2
+  // (added in the epilogue) whenever the 512 TMEM columns allow it.
+  constexpr bool USE_C2 = 2 * (D2C + 2 * D2W) <= 512;
+  constexpr int C2C = D2C + D2W;
+  constexpr int TILE_COLS = D2C + (USE_C2 ? 2 : 1) * D2W;
+  static_assert(2 * TILE_COLS <= 512, "two row tiles must fit the 512 TMEM columns");
+  static_assert((K1PMAX - DH) % 8 == 0 && DH % 8 == 0, "u is written in 8-column pieces");
+
+  extern __shared__ __align__(128) float sm[];
+  float* w1buf = sm;
+  float* w2buf = sm + a.w1_floats;
+  // w2buf also holds, after the W2 blocks, the b2 images: per net [hi | lo] of an [NTP x 8] operand whose only
+  // non-zero column multiplies the constant-one column of u, so that GEMM2 starts from the bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w2buf + a.w2_floats);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.H, Cd = a.Cd, D = 2 * DH;
+  const int NC = H / CU;
+  const int NCS = NETSEQ ? 2 * NC : NC;              // chunk steps per layer
+  const int K1P = (DH + Cd + 1 + 7) & ~7;
+  const int nL = a.l1 - a.l0;
+
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bars[B_W1F], 1); mbar_init(&bars[B_W1E], 1); mbar_init(&bars[B_W2F], 1); mbar_init(&bars[B_W2E], 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bars[B_UF0 + g], 128); mbar_init(&bars[B_D1F0 + g], 1);
+      mbar_init(&bars[B_AF0 + g], 128); mbar_init(&bars[B_D2F0 + g], 1);
+    }
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const int my_pairs = (a.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ph1 = 0, ph2 = 0;
+      long long step = 0;
+      const uint32_t w1_bytes = (uint32_t)(4 * H * K1P) * 4u;          // actual image size for this Cd
+      const uint32_t w2_bytes = (uint32_t)a.w2_floats * 4u;
+      for (int it = 0; it < my_pairs; ++it)
+        for (int li = 0; li < nL; ++li, ++step) {
+          const int i = MODE == 0 ? a.l0 + li : a.l1 - 1 - li;
+          const float* src = a.wimg + (size_t)i * a.layer_floats;
+          if (step > 0) { mbar_wait(&bars[B_W1E], ph1); ph1 ^= 1; }
+          mbar_expect_tx(&bars[B_W1F], w1_bytes);
+          bulk_g2s(w1buf, src, w1_bytes, &bars[B_W1F]);
+          if (step > 0) { mbar_wait(&bars[B_W2E], ph2); ph2 ^= 1; }
+          mbar_expect_tx(&bars[B_W2F], w2_bytes);
+          bulk_g2s(w2buf, src + a.w1_floats, w2_bytes, &bars[B_W2F]);
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // The whole warp runs this role (warp-uniform control flow and descriptor arithmetic, so the descriptors
+    // live in uniform registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    uint32_t ph_w1 = 0, ph_w2 = 0, ph_u[2] = {0, 0}, ph_a[2] = {0, 0};
+    const uint32_t idesc1 = idesc_tf32(128, D1W), idesc2 = idesc_tf32(128, NTP);
+    const uint32_t lbo = (128u >> 4) << 16;
+    const uint32_t w1_lo = ((smem_u32(w1buf) & 0x3FFFFu) >> 4) | lbo, w2_lo = ((smem_u32(w2buf) & 0x3FFFFu) >> 4) | lbo;
+    const uint32_t hi1 = ((uint32_t)(K1P >> 2) * 128u >> 4) | (1u << 14);       // SBO, descriptor version 1
+    const uint32_t hi2 = ((uint32_t)(CU >> 2) * 128u >> 4) | (1u << 14);
+    const uint32_t hib = (256u >> 4) | (1u << 14);                              // b2 images: K = 8
+    const uint32_t chunk1 = (uint32_t)(D1W * K1P) * 4u >> 4;                 // one hi (or lo) W1 chunk image, in 16 B units
+    const uint32_t blk2 = (uint32_t)(NTP * CU) * 4u >> 4;                       // one hi (or lo) W2 (chunk, net) image
+    const uint32_t b2_lo = w2_lo + ((uint32_t)(4 * NTP * H) * 4u >> 4);         // b2 images follow the W2 blocks
+    const uint32_t blkb = (uint32_t)(NTP * 8) * 4u >> 4;
+    const int nk1 = K1P >> 3;
+    const int k_one = (DH + Cd) & ~7;                                           // u slice holding the constant one
+    const bool leader = elect_one();
+    auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    // GEMM1 chunk c of tile g: D1 = [u_lo*W1_hi + u_hi*W1_lo] + u_hi*W1_hi   (corrections first)
+    auto gemm1 = [&](int g, int c) {
+      const uint32_t tb = tbase + (uint32_t)(g * TILE_COLS);
+      const uint32_t bh = w1_lo + (uint32_t)(2 * c) * chunk1, bl = bh + chunk1;
+#pragma unroll
+      for (int j = 0; j < K1PMAX / 8; ++j)
+        if (j < nk1) mma_tf32_ts(tb + D1C, tb + U_LO + 8 * j, desc(bh + 16u * j, hi1), idesc1, j ? 1u : 0u);
+#pragma unroll
+      for (int j = 0; j < K1PMAX / 8; ++j)
+        if (j < nk1) mma_tf32_ts(tb + D1C, tb + U_HI + 8 * j, desc(bl + 16u * j, hi1), idesc1, 1u);
+#pragma unroll
+      for (int j = 0; j < K1PMAX / 8; ++j)
+        if (j < nk1) mma_tf32_ts(tb + D1C, tb + U_HI + 8 * j, desc(bh + 16u * j, hi1), idesc1, 1u);
+    };
+    // GEMM2 of chunk step cc of tile g: main products into D2 (seeded with b2), corrections into C2
+    auto gemm2_net = [&](uint32_t tb, int net, int c, uint32_t d2, uint32_t c2, uint32_t ah, uint32_t al) {
+      const uint32_t bh = w2_lo + (uint32_t)((c * 2 + net) * 2) * blk2, bl = bh + blk2;
+      if (c == 0) {     // D2 = 1 * b2 (hi image overwrites, lo image accumulates)
+        mma_tf32_ts(d2, tb + U_HI + k_one, desc(b2_lo + (uint32_t)(net * 2) * blkb, hib), idesc2, 0u);
+        mma_tf32_ts(d2, tb + U_HI + k_one, desc(b2_lo + (uint32_t)(net * 2 + 1) * blkb, hib), idesc2, 1u);
+      }
+#pragma unroll
+      for (int j = 0; j < CU / 8; ++j)
+        mma_tf32_ts(c2, al + 8 * j, desc(bh + 16u * j, hi2), idesc2, (USE_C2 && c == 0 && j == 0) ? 0u : 1u);
+#pragma unroll
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(c2, ah + 8 * j, desc(bl + 16u * j, hi2), idesc2, 1u);
+#pragma unroll
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(d2, ah + 8 * j, desc(bh + 16u * j, hi2), idesc2, 1u);
+    };
+    auto gemm2 = [&](int g, int cc) {
+      const uint32_t tb = tbase + (uint32_t)(g * TILE_COLS);
+      if (NETSEQ) {
+        const int net = cc >= NC ? 1 : 0;
+        gemm2_net(tb, net, cc - net * NC, tb + D2C, USE_C2 ? tb + C2C : tb + D2C, tb + D1C, tb + A_LO);
+      } else {
+#pragma unroll
+        for (int net = 0; net < 2; ++net)
+          gemm2_net(tb, net, cc, tb + D2C + net * NTP, USE_C2 ? tb + C2C + net * NTP : tb + D2C + net * NTP,
+                    tb + D1C + net * CU, tb + A_LO + net * CU);
+      }
+    };
+    for (int it = 0; it < my_pairs; ++it)
+      for (int li = 0; li < nL; ++li) {
+        mbar_wait(&bars[B_W1F], ph_w1); ph_w1 ^= 1;
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&bars[B_UF0 + g], ph_u[g]); ph_u[g] ^= 1;
+          fence_after_sync();
+          if (leader) {
+            gemm1(g, 0);
+            if (NCS == 1 && g == 1) mma_commit(&bars[B_W1E]);
+            mma_commit(&bars[B_D1F0 + g]);
+          }
+          __syncwarp();
+        }
+        for (int cc = 0; cc < NCS; ++cc)
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&bars[B_AF0 + g], ph_a[g]); ph_a[g] ^= 1;
+            if (cc == 0 && g == 0) { mbar_wait(&bars[B_W2F], ph_w2); ph_w2 ^= 1; }
+            fence_after_sync();
+            if (leader) {
+              gemm2(g, cc);
+              if (cc + 1 < NCS) {
+                gemm1(g, cc + 1);
+                if (cc + 2 == NCS && g == 1) mma_commit(&bars[B_W1E]);   // last GEMM1 of the layer issued
+                mma_commit(&bars[B_D1F0 + g]);
+              }
+              if (cc + 1 == NCS && g == 1) mma_commit(&bars[B_W2E]);     // last GEMM2 of the layer issued
+              if (cc + 1 == NCS || (NETSEQ && cc + 1 == NC)) mma_commit(&bars[B_D2F0 + g]);
+            }
+            __syncwarp();
+          }
+      }
+  } else {
+    // ------------------------------------------------------------------ epilogue: one thread per row
+    const int g = (warp - 2) >> 2;                      // tile of the pair
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const uint32_t trow = tbase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * TILE_COLS);
+    uint32_t ph_d1 = 0, ph_d2 = 0;
+    for (int it = 0; it < my_pairs; ++it) {
+      const long long pair = (long long)blockIdx.x + (long long)it * gridDim.x;
+      const long long row = pair * 256 + g * 128 + quarter * 32 + lane;
+      const bool valid = row < a.N;
+      const long long src = valid ? (a.idx ? a.idx[row] : row) : 0;
+      float xa[DH], xb[DH], cc[CDMAX], ld = 0.0f;       // even features, odd features, condition
+#pragma unroll
+      for (int m = 0; m < DH / 2; ++m) {
+        float4 v = valid ? __ldg(reinterpret_cast<const float4*>(a.X + src * D) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xa[2 * m] = v.x; xb[2 * m] = v.y; xa[2 * m + 1] = v.z; xb[2 * m + 1] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < CDMAX; ++k) cc[k] = (valid && k < Cd) ? __ldg(a.C + src * Cd + k) : 0.0f;
+      // static part of u: [c | 1 | 0...] at columns DH.. of U_HI / U_LO (written once per tile)
+#pragma unroll
+      for (int e0 = 0; e0 < K1PMAX - DH; e0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = e0 + j;
+          float v = 0.0f;
+          if (k < CDMAX && k < Cd) v = cc[k < CDMAX ? k : 0];
+          if (k == Cd) v = 1.0f;
+          split_tf32(v, hi[j], lo[j]);
+        }
+        tmem_st_x8(trow + U_HI + DH + e0, hi);
+        tmem_st_x8(trow + U_LO + DH + e0, lo);
+      }
+
+      auto layer = [&](float (&xT)[DH], float (&xK)[DH], int li) {
+        // ---- u (conditioning half) -> TMEM
+#pragma unroll
+        for (int e0 = 0; e0 < DH; e0 += 8) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_tf32(xK[e0 + j], hi[j], lo[j]);
+          tmem_st_x8(trow + U_HI + e0, hi);
+          tmem_st_x8(trow + U_LO + e0, lo);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        mbar_arrive(&bars[B_UF0 + g]);
+        // ---- hidden chunks: D1 -> act -> (A_hi in place, A_lo); NETSEQ: nn_t chunks, park t, nn_s chunks
+        float tpark[NETSEQ ? DH : 1];
+        for (int cc = 0; cc < NCS; ++cc) {
+          mbar_wait(&bars[B_D1F0 + g], ph_d1); ph_d1 ^= 1;
+          fence_after_sync();
+          if (DH >= 32) {                        // register budget: 16-column pieces for the wide rows
+#pragma unroll
+            for (int q0 = 0; q0 < D1W; q0 += 16) {
+              uint32_t r[16], lo[16];
+              tmem_ld_x16(trow + D1C + q0, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float h = act_mma<ACT>(__uint_as_float(r[j]));
+                split_tf32(h, r[j], lo[j]);
+              }
+              tmem_st_x16(trow + D1C + q0, r);
+              tmem_st_x16(trow + A_LO + q0, lo);
+            }
+          } else {
+#pragma unroll
+            for (int q0 = 0; q0 < D1W; q0 += 32) {
+              uint32_t r[32], lo[32];
+              tmem_ld_x32(trow + D1C + q0, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float h = act_mma<ACT>(__uint_as_float(r[j]));
+                split_tf32(h, r[j], lo[j]);
+              }
+              tmem_st_x32(trow + D1C + q0, r);
+              tmem_st_x32(trow + A_LO + q0, lo);
+            }
+          }
+          tmem_wait_st();
+          fence_before_sync();
+          mbar_arrive(&bars[B_AF0 + g]);
+          if (NETSEQ && cc + 1 == NC) {          // nn_t complete: t = D2 + C2 into registers
+            mbar_wait(&bars[B_D2F0 + g], ph_d2); ph_d2 ^= 1;
+            fence_after_sync();
+#pragma unroll
+            for (int e0 = 0; e0 < DH; e0 += 16) {
+              uint32_t tv[16], tc[16];
+              tmem_ld_x16(trow + D2C + e0, tv);
+              if (USE_C2) tmem_ld_x16(trow + C2C + e0, tc);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                tpark[NETSEQ ? e0 + j : 0] = USE_C2 ? __uint_as_float(tv[j]) + __uint_as_float(tc[j]) : __uint_as_float(tv[j]);
+            }
+            fence_before_sync();                 // the nn_s GEMM2 will overwrite D2 / C2 after the next a_full arrival
+          }
+        }
+        // ---- t, s -> coupling
+        mbar_wait(&bars[B_D2F0 + g], ph_d2); ph_d2 ^= 1;
+        fence_after_sync();
+#pragma unroll
+        for (int e0 = 0; e0 < DH; e0 += 16) {
+          uint32_t tv[16], sv[16], tc[16], sc[16];
+          constexpr int SOFF = NETSEQ ? 0 : NTP;               // where s sits inside D2 / C2
+          if (!NETSEQ) tmem_ld_x16(trow + D2C + e0, tv);
+          tmem_ld_x16(trow + D2C + SOFF + e0, sv);
+          if (USE_C2) {
+            if (!NETSEQ) tmem_ld_x16(trow + C2C + e0, tc);
+            tmem_ld_x16(trow + C2C + SOFF + e0, sc);
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t;
+            if (NETSEQ) t = tpark[NETSEQ ? e0 + j : 0];
+            else t = USE_C2 ? __uint_as_float(tv[j]) + __uint_as_float(tc[j]) : __uint_as_float(tv[j]);
+            const float s = USE_C2 ? __uint_as_float(sv[j]) + __uint_as_float(sc[j]) : __uint_as_float(sv[j]);
+            if (MODE == 0) { xT[e0 + j] = fmaf(xT[e0 + j], expf(s), t); ld += s; }
+            else xT[e0 + j] = (xT[e0 + j] - t) * expf(-s);
+          }
+        }
+      };
+      for (int li = 0; li < nL; ++li) {
+        const int i = MODE == 0 ? a.l0 + li : a.l1 - 1 - li;
+        if ((i & 1) == 0) layer(xa, xb, li);             // even layer transforms the even features
+        else layer(xb, xa, li);
+      }
+
+      if (valid) {
+        if (a.out_x) {
+#pragma unroll
+          for (int m = 0; m < DH / 2; ++m)
+            reinterpret_cast<float4*>(a.out_x + row * D)[m] = make_float4(xa[2 * m], xb[2 * m], xa[2 * m + 1], xb[2 * m + 1]);
+        }
+        if (MODE == 0) {
+          float q = 0.0f;
+#pragma unroll
+          for (int e = 0; e < DH; ++e) { q = fmaf(xa[e], xa[e], q); q = fmaf(xb[e], xb[e], q); }
+          if (a.out_logdet) a.out_logdet[row] = ld;
+          if (a.out_logp) a.out_logp[row] = ld - 0.5f * (D * 1.8378770664093453f + q);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+template <int DH, int CDMAX, int CU, bool NETSEQ>
+cudaError_t launch_mma_shape(int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+#define RNVP_MMA_LAUNCH(ACT_, MODE_)                                                                        \
+  {                                                                                                          \
+    auto k = rnvp_mma_kernel<DH, CDMAX, CU, NETSEQ, ACT_, MODE_>;                                                    \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    if (e != cudaSuccess) return e;                                                                          \
+    k<<<grid, MMA_THREADS, smem, st>>>(a);                                                                   \
+    return cudaGetLastError();                                                                               \
+  }
+  if (act == 1 && mode == 0) RNVP_MMA_LAUNCH(1, 0)
+  if (act == 1 && mode == 1) RNVP_MMA_LAUNCH(1, 1)
+  if (act == 2 && mode == 0) RNVP_MMA_LAUNCH(2, 0)
+  if (act == 2 && mode == 1) RNVP_MMA_LAUNCH(2, 1)
+#undef RNVP_MMA_LAUNCH
+  return cudaErrorInvalidValue;
+}
+
 }  // namespace
+
+size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats) {
+  return (size_t)(w1_floats + w2_floats) * 4 + 8 * B_COUNT + 64;
+}
+
+cudaError_t rnvp_launch_mma(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+  if (DH == 16) return launch_mma_shape<16, 8, 32, false>(act, mode, a, grid, smem, st);
+  if (DH == 32) return launch_mma_shape<32, 16, 32, true>(act, mode, a, grid, smem, st);
+  return cudaErrorInvalidValue;
+}
 
 cudaError_t rnvp_launch_mma_selftest(const float* A, const float* B, float* D, int N, int K, int passes, cudaStream_t st) {
   const size_t smem = (size_t)2 * N * K * sizeof(float);

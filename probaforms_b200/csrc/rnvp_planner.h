@@ -47,6 +47,14 @@ struct FlowGeom {
   bool small_ok = false;
   int sNE = 0, sNC = 0, srec = 0, snet = 0, small_floats = 0;
   int64_t small_off = 0;
+  int64_t packed_gather = 0;     // floats covered by the plain gather map p2f (tile + small layouts)
+  // tcgen05 layout (rnvp_mma.cu): one hidden layer, even D with D/2 in {16,32}; TF32 hi/lo images of the
+  // weights in the no-swizzle K-major core-matrix layout, per layer [W1 chunks | W2 chunks | b2]
+  bool mma_ok = false;
+  int mDH = 0, mCDMAX = 0, mCU = 0, mK1P = 0, mNTP = 0;
+  bool m_netseq = false;
+  int m_w1_floats = 0, m_w2_floats = 0, m_b2_floats = 0, m_layer_floats = 0;
+  int64_t mma_off = 0, mma_floats = 0;
 };
 
 // ------------------------------------------------------------------ layout
@@ -102,6 +110,84 @@ inline void build_layout(FlowGeom* d) {
       d->packed = d->small_off + total;
     }
   }
+  d->packed_gather = d->packed;
+  // tcgen05 layout
+  d->mma_ok = false;
+  if (nh == 1 && D % 2 == 0 && (D / 2 == 16 || D / 2 == 32)) {
+    const int DH = D / 2, H = d->hidden[0];
+    const int CDMAX = DH == 16 ? 8 : 16, CU = 32;
+    const bool netseq = DH == 32;                              // nn_t chunks before nn_s chunks (rnvp_mma.cu)
+    const int K1P = (DH + Cd + 1 + 7) & ~7, NTP = (DH + 15) & ~15;
+    const int tile_cols = netseq ? 2 * K1P + 2 * CU + 2 * NTP : 2 * K1P + 4 * CU + 4 * NTP;
+    const int64_t w1 = (int64_t)4 * H * K1P, w2 = (int64_t)4 * NTP * H;
+    if (Cd <= CDMAX && H % CU == 0 && H >= CU && tile_cols <= 256 && (w1 + w2 + 32 * NTP) * 4 + 2048 <= d->max_smem) {
+      d->mma_ok = true;
+      d->mDH = DH; d->mCDMAX = CDMAX; d->mCU = CU; d->mK1P = K1P; d->mNTP = NTP; d->m_netseq = netseq;
+      d->m_b2_floats = 32 * NTP;                               // 2 nets x [hi | lo] x [NTP x 8]
+      d->m_w1_floats = (int)w1; d->m_w2_floats = (int)w2 + d->m_b2_floats;  // b2 images ride with the W2 copy
+      d->m_layer_floats = d->m_w1_floats + d->m_w2_floats;
+      d->mma_off = (d->packed + 31) & ~(int64_t)31;            // 128-byte aligned for the bulk copies
+      d->mma_floats = (int64_t)d->L * d->m_layer_floats;
+      d->packed = d->mma_off + d->mma_floats;
+    }
+  }
+}
+
+// float offset of element (n, k) of an [N x K] K-major MMA operand in the no-swizzle core-matrix layout
+// (8 rows x 16 B core matrices, 128 B each, K-adjacent core matrices contiguous): see tc05.cuh
+inline int mma_tiled_off(int n, int k, int K) { return (n >> 3) * (K >> 2) * 32 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
+
+// map of the tcgen05 region: value = 4*flat_index + code (0: TF32 hi image, 1: lo remainder, 2: full fp32), or -1 (zero)
+inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
+  m2f.assign(d->mma_ok ? d->mma_floats : 0, -1);
+  if (!d->mma_ok) return;
+  const int D = d->D, Cd = d->Cd, H = d->hidden[0], DH = d->mDH, CU = d->mCU, K1P = d->mK1P, NTP = d->mNTP;
+  const int NC = H / CU;
+  for (int i = 0; i < d->L; ++i) {
+    const LayerGeom& lg = d->layers[i];
+    const LinearGeom& g0 = lg.lin[0];
+    const LinearGeom& g1 = lg.lin[1];
+    const int64_t base = (int64_t)i * d->m_layer_floats;
+    // W1 image: one block [hi | lo] per chunk step.  Concurrent nets: block c has rows 0..CU-1 = t units and
+    // CU..2CU-1 = s units of chunk c.  NETSEQ: blocks 0..NC-1 are the t chunks, NC..2NC-1 the s chunks (CU rows each).
+    const int rows1 = d->m_netseq ? CU : 2 * CU, nblk1 = d->m_netseq ? 2 * NC : NC;
+    for (int cc = 0; cc < nblk1; ++cc)
+      for (int part = 0; part < 2; ++part) {
+        const int64_t blk = base + ((int64_t)cc * 2 + part) * (rows1 * K1P);
+        for (int n = 0; n < rows1; ++n) {
+          const int net = d->m_netseq ? cc / NC : n / CU;
+          const int unit = (d->m_netseq ? cc % NC : cc) * CU + n % CU;
+          for (int k = 0; k < K1P; ++k) {
+            int64_t f = -1;
+            if (k < DH) f = g0.flat_w[net] + (int64_t)unit * (D + Cd) + (lg.par == 0 ? 2 * k + 1 : 2 * k);
+            else if (k < DH + Cd) f = g0.flat_w[net] + (int64_t)unit * (D + Cd) + D + (k - DH);
+            else if (k == DH + Cd) f = g0.flat_b[net] + unit;
+            if (f >= 0) m2f[blk + mma_tiled_off(n, k, K1P)] = (int)(4 * f + part);
+          }
+        }
+      }
+    // W2 image: chunk c, net, [hi | lo]: rows = transformed features, cols = units of the chunk
+    const int64_t base2 = base + d->m_w1_floats;
+    for (int c = 0; c < NC; ++c)
+      for (int net = 0; net < 2; ++net)
+        for (int part = 0; part < 2; ++part) {
+          const int64_t blk = base2 + (((int64_t)c * 2 + net) * 2 + part) * (NTP * CU);
+          for (int r = 0; r < DH; ++r) {
+            const int ft = lg.par == 0 ? 2 * r : 2 * r + 1;
+            for (int kk = 0; kk < CU; ++kk)
+              m2f[blk + mma_tiled_off(r, kk, CU)] = (int)(4 * (g1.flat_w[net] + (int64_t)ft * H + c * CU + kk) + part);
+          }
+        }
+    // b2 images: per net [hi | lo] of an [NTP x 8] operand; column (DH+Cd)%8 holds b2, the rest is zero.  Multiplied
+    // with the 8-column u slice that contains the constant one it seeds the GEMM2 accumulator with the bias.
+    const int64_t base3 = base2 + (int64_t)4 * NTP * H;
+    for (int net = 0; net < 2; ++net)
+      for (int part = 0; part < 2; ++part)
+        for (int r = 0; r < DH; ++r) {
+          const int ft = lg.par == 0 ? 2 * r : 2 * r + 1;
+          m2f[base3 + (net * 2 + part) * (NTP * 8) + mma_tiled_off(r, (DH + Cd) & 7, 8)] = (int)(4 * (g1.flat_b[net] + ft) + part);
+        }
+  }
 }
 
 // second flat -> packed map: position of each parameter in the small-flow layout (or -1)
@@ -136,7 +222,7 @@ inline void build_small_map(const FlowGeom* d, std::vector<int>& p2f, std::vecto
 }
 
 inline void build_maps(const FlowGeom* d, std::vector<int>& p2f, std::vector<int>& f2p) {
-  p2f.assign(d->packed, -1);
+  p2f.assign(d->packed_gather, -1);
   f2p.assign(d->P, -1);
   const int D = d->D, nh = d->nh;
   for (int i = 0; i < d->L; ++i) {

@@ -48,6 +48,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMEM allocation (one full warp executes these)
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
@@ -133,12 +140,14 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_nosw(uint32_t smem_addr, ui
          (1ull << 46);
 }
 
-// round-to-nearest tf32 "hi" part and fp32 remainder: v = hi + lo exactly
+// v ~= hi + lo with both parts exactly representable in TF32 (round-to-nearest-away): the tensor core would
+// otherwise TRUNCATE the fp32 remainder to 10 mantissa bits, a biased 2^-21 relative error; rounded it is 2^-23
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  uint32_t h;
+  uint32_t h, l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));
   hi = h;
-  lo = __float_as_uint(v - __uint_as_float(h));
+  lo = l;
 }
 
 }  // namespace tc05

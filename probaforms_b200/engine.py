@@ -55,9 +55,10 @@ class FlowEngine:
         self.packed = torch.zeros(self.n_packed, **kw)    # mask-compacted, padded kernel layout
         # gradient accumulator; the float after it is the loss slot (sum of logp over rows), so a
         # single all-reduce moves gradients and loss together
-        self._gbuf = torch.zeros(self.n_packed + 4, **kw)
-        self.gpacked = self._gbuf[: self.n_packed]
-        self.loss_slot = self._gbuf[self.n_packed: self.n_packed + 1]
+        self.n_grad = int(self.lib.rnvp_grad_count(self._desc))
+        self._gbuf = torch.zeros(self.n_grad + 4, **kw)
+        self.gpacked = self._gbuf[: self.n_grad]
+        self.loss_slot = self._gbuf[self.n_grad: self.n_grad + 1]
         self.exp_avg = None
         self.exp_avg_sq = None
         self.adam_steps = 0
@@ -101,6 +102,10 @@ class FlowEngine:
             _lib.check(self.lib.rnvp_plan_info(self._desc, mode, C.byref(tr), C.byref(sb), C.byref(no), C.byref(fam)),
                        "rnvp_plan_info")
         return {"tile_rows": tr.value, "smem_bytes": sb.value, "n_ops": no.value, "kernel_family": fam.value}
+
+    def set_path(self, path):
+        """0 auto (tcgen05 TF32x3 kernels where eligible), 1 FP32-FMA kernels only."""
+        _lib.check(self.lib.rnvp_set_path(self._desc, int(path)), "rnvp_set_path")
 
     def workspace(self):
         if self._workspace is None:

@@ -206,9 +206,9 @@ extern "C" int rnvp_emulate(int mode, int D, int Cd, int L, int nh, const int* h
   const float nan = std::numeric_limits<float>::quiet_NaN();
   e.sm.assign(b.sm.total_floats, nan);
   e.stash.assign(b.stash_per_cta, nan);
-  e.packed.assign(g.packed, 0.f);
-  for (int64_t p = 0; p < g.packed; ++p) e.packed[p] = p2f[p] >= 0 ? flat[p2f[p]] : 0.f;
-  e.gpacked.assign(g.packed, 0.f);
+  e.packed.assign(g.packed_gather, 0.f);
+  for (int64_t p = 0; p < g.packed_gather; ++p) e.packed[p] = p2f[p] >= 0 ? flat[p2f[p]] : 0.f;
+  e.gpacked.assign(g.packed_tile, 0.f);
   for (long long row0 = 0; row0 < N; row0 += b.R) e.run_tile(row0);
   if (gflat) for (int64_t f = 0; f < g.P; ++f) gflat[f] = f2p[f] >= 0 ? e.gpacked[f2p[f]] : 0.f;
   if (loss_sum) *loss_sum = e.loss_sum;

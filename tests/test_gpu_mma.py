@@ -30,3 +30,36 @@ def test_tcgen05_selftest(N, K):
     print(f"N={N} K={K}: tf32 {errs[1]:.2e}  tf32x3 {errs[3]:.2e}  torch-fp32 {fp32:.2e}")
     assert errs[1] < 2e-3           # plain TF32: ~2^-11 per operand
     assert errs[3] < 2e-6           # split: fp32-grade
+
+
+@pytest.mark.parametrize("shape", [(32, 8, 16, 128), (64, 16, 24, 128), (32, 0, 3, 64), (32, 5, 4, 256), (64, 16, 2, 32)])
+@pytest.mark.parametrize("N", [1, 255, 257, 40000])
+def test_tcgen05_flow_matches_fp32_kernels(shape, N):
+    """The tcgen05 (TF32x3) forward / inverse kernels against the FP32-FMA tile kernels of the same
+    library and the g(f(x)) round trip; tolerance rel 1e-5 like every other parity test."""
+    from probaforms_b200.models import RealNVPLayer, NormalizingFlow
+    D, Cd, L, H = shape
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    nf = NormalizingFlow([RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, (H,), "tanh") for i in range(L)], None).to(dev)
+    eng = nf._fused()
+    assert eng.plan_info(0)["kernel_family"] == 2
+    g = torch.Generator().manual_seed(N)
+    X = torch.randn(N, D, generator=g).to(dev)
+    Cn = torch.randn(N, Cd, generator=g).to(dev) if Cd else None
+    eps = torch.randn(N, D, generator=g).to(dev)
+    z, ld, lp = eng.forward(X, Cn)
+    x_back = eng.inverse(z, Cn)
+    xs = eng.inverse(eps, Cn)
+    eng.set_path(1)
+    assert eng.plan_info(0)["kernel_family"] == 0
+    z0, ld0, lp0 = eng.forward(X, Cn)
+    xs0 = eng.inverse(eps, Cn)
+    eng.set_path(0)
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    print(f"shape {shape} N={N}: z {rel(z, z0):.2e} logdet {rel(ld, ld0):.2e} logp {rel(lp, lp0):.2e} sample {rel(xs, xs0):.2e}")
+    assert rel(z, z0) < 1e-5 and rel(lp, lp0) < 1e-5 and rel(ld, ld0) < 1e-5
+    assert rel(xs, xs0) < 1e-5
+    assert float((x_back - X).abs().max()) < 1e-4 * max(1.0, float(X.abs().max()))

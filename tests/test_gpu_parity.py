@@ -261,8 +261,12 @@ def test_gradient_is_additive_over_row_shards(dev):
     lp_b = torch.empty(N, device=dev)
     eng.backward(X, C, None, N, -1.0 / N, logp_rows=lp_b)
     eng.zero_grads()
+    eng.set_path(1)                                  # FP32-FMA forward kernel: same arithmetic, bit-equal
     lp_f = eng.forward(X, C, want_z=False, want_logdet=False)[2]
     assert torch.equal(lp_b, lp_f)
+    eng.set_path(0)                                  # tcgen05 TF32x3 forward kernel: within the fp32 tolerance
+    lp_t = eng.forward(X, C, want_z=False, want_logdet=False)[2]
+    assert float((lp_t - lp_f).abs().max()) < 1e-5 * float(lp_f.abs().max())
 
 
 def test_error_behaviour(dev):
