@@ -238,6 +238,49 @@ def main():
     rows_per_s = n_global * K / (total_ms * 1e-3)
     final_loss = float(losses[W + K - 1])
 
+    # ---- the other two passes of the metric on the same flow: per-row log-prob and sample (no communication)
+    def time_pass(fn, rows, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return rows * world / (float(t) * 1e-3), float(t)
+
+    def pass_rates(engine, Xr, Cr):
+        n = Xr.shape[0]
+        lp = torch.empty(n, device=dev)
+        out = torch.empty_like(Xr)
+        r_lp, ms_lp = time_pass(lambda: engine.lib.rnvp_forward(
+            engine._desc, engine.packed.data_ptr(), Xr.data_ptr(), Cr.data_ptr() if Cr is not None else None, None, n,
+            0, engine.L, None, None, lp.data_ptr(), None), n)
+        r_s, ms_s = time_pass(lambda: engine.inverse(Xr, Cr, out=out), n)
+        return r_lp, ms_lp, r_s, ms_s
+
+    n_pass = min(n_res, 1 << 20)
+    lp_rate, lp_ms, s_rate, s_ms = pass_rates(eng, X[:n_pass], None if C is None else C[:n_pass])
+    fam = {0: "fp32 tile kernel", 1: "small-flow kernel", 2: "tcgen05 TF32x3 kernel"}[eng.plan_info(0)["kernel_family"]]
+
+    # ---- configs[1] (c2): 2-D moons flow, per-row log-prob and sample, 16.7 M rows per GPU
+    D2, Cd2, L2, hid2, _, desc2 = WORKLOADS["c2"]
+    torch.manual_seed(0)
+    nf2 = NormalizingFlow([RealNVPLayer(D2, Cd2, (torch.arange(D2) + i) % 2, hid2, "tanh") for i in range(L2)],
+                          prior=None).to(dev)
+    eng2 = nf2._fused()
+    n2 = 1 << 24
+    X2 = torch.randn(n2, D2, device=dev, generator=gen)
+    C2 = (torch.rand(n2, Cd2, device=dev, generator=gen) > 0.5).float()
+    c2_lp, c2_lp_ms, c2_s, c2_s_ms = pass_rates(eng2, X2, C2)
+    del X2, C2
+
     # ---- end to end through the public API with pinned host arrays
     e2e = None
     if not args.no_e2e:
@@ -299,6 +342,23 @@ def main():
                          "hbm_frac_of_measured": per_gpu * bytes_row / (kms * 1e-3) / 1e9 / hbm_peak},
             "gpu_launches": launches, "clocks": clocks,
         }
+        mufu_peak = 16 * sms * sm_max * 1e6                             # MUFU lanes/s: the tanh (ex2 + rcp) pipe
+        n_tanh = 2 * H * L
+        line["phases"] = {
+            "log_prob": {"value": lp_rate, "unit": "rows/s", "kernel": fam, "rows_per_launch": n_pass, "kernel_ms": lp_ms,
+                         "flops_per_row": f_fwd, "frac_of_fp32_fma_peak": lp_rate / world * f_fwd / 1e12 / fp32_peak,
+                         "frac_of_mufu_peak": lp_rate / world * 2 * n_tanh / mufu_peak},
+            "sample": {"value": s_rate, "unit": "rows/s", "kernel": fam, "rows_per_launch": n_pass, "kernel_ms": s_ms,
+                       "flops_per_row": f_fwd, "frac_of_fp32_fma_peak": s_rate / world * f_fwd / 1e12 / fp32_peak,
+                       "frac_of_mufu_peak": s_rate / world * 2 * n_tanh / mufu_peak,
+                       "note": "latent noise read from HBM (parity mode)"},
+        }
+        f2_fwd, _ = flops_per_row(D2, Cd2, L2, hid2[0])
+        line["also"] = {"c2 -- " + desc2: {
+            "log_prob_rows_s": c2_lp, "sample_rows_s": c2_s, "rows_per_launch": n2, "kernel": "small-flow kernel (row per thread)",
+            "frac_of_mufu_peak": c2_lp / world * 2 * (2 * hid2[0] * L2) / mufu_peak,
+            "frac_of_fp32_fma_peak": c2_lp / world * f2_fwd / 1e12 / fp32_peak,
+            "hbm_gbs": c2_lp / world * 16 / 1e9}}
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -123,11 +123,9 @@ __global__ void pack_mma_kernel(const float* __restrict__ flat, float* __restric
     float out = 0.0f;
     if (m >= 0) {
       const float v = flat[m >> 2];
-      uint32_t h;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+      const uint32_t h = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;          // round_tf32, see tc05.cuh
+      const uint32_t l = (__float_as_uint(v - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;
       const int code = m & 3;
-      uint32_t l;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - __uint_as_float(h)));
       out = code == 0 ? __uint_as_float(h) : (code == 1 ? __uint_as_float(l) : v);
     }
     img[i] = out;
