@@ -333,7 +333,9 @@ def main():
                        "final_loss": final_loss},
             "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak, "traffic": None,
-                         "kernel": "rnvp_tile_kernel<TR,2> (fused forward+backward)", "kernel_ms": kms,
+                         "kernel": ("rnvp_mma_kernel<..,2> (tcgen05 forward sweep) + rnvp_tile_kernel<TR,3> (FP32 backward sweep)"
+                                    if eng._bwd_two_kernels else "rnvp_tile_kernel<TR,2> (fused forward+backward)"),
+                         "kernel_ms": kms,
                          "kernel_share_of_step": kms / (total_ms / K),
                          "flops_per_row": f_fit, "rows_per_launch": per_gpu,
                          "peak_source": f"2*128 lanes*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "

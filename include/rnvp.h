@@ -55,12 +55,15 @@ void rnvp_desc_destroy(rnvp_desc* d);
 int64_t rnvp_param_count(const rnvp_desc* d);    /* P: flat reference-layout parameters */
 int64_t rnvp_packed_count(const rnvp_desc* d);   /* kernel-private packed layouts (all kernel families) */
 int64_t rnvp_grad_count(const rnvp_desc* d);     /* floats of the packed gradient accumulator d_gpacked */
-/* bytes of scratch rnvp_backward needs (x_T stash; stays L2 resident) */
-int64_t rnvp_workspace_bytes(const rnvp_desc* d);
+/* bytes of scratch rnvp_backward needs for a batch of N rows: the per-CTA x_T stash of the fused FP32 kernel
+ * (independent of N, stays L2 resident) or, on the tcgen05 path, z plus the per-layer (x_T, s) stash of the
+ * tensor-core forward sweep, N*(D + L*D)*4 bytes */
+int64_t rnvp_workspace_bytes(const rnvp_desc* d, int64_t N);
 /* offsets[2*k], offsets[2*k+1] = (float offset, numel) of the k-th tensor of nf.parameters();
  * n = 4*(n_hidden+1)*L entries pairs.  Returns the number of tensors. */
 int rnvp_param_tensors(const rnvp_desc* d, int64_t* offsets, int max_tensors);
-/* rows per CTA tile chosen for mode 0/1/2, and CTAs launched for N rows (introspection / bench) */
+/* plan introspection: mode 0 forward, 1 inverse, 2 fused forward+backward, 3 backward-only sweep (used after the
+ * tcgen05 forward); rows per CTA tile, shared memory, ops per tile, kernel family (0 tile, 1 small-flow, 2 tcgen05) */
 int rnvp_plan_info(const rnvp_desc* d, int mode, int* tile_rows, int* smem_bytes, int* n_ops, int* kernel_family);
 
 /* flat (reference layout) -> packed; run after every parameter update */

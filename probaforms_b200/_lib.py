@@ -27,7 +27,7 @@ SIGNATURES = {
     "rnvp_param_count": (C.c_int64, [c_desc_p]),
     "rnvp_packed_count": (C.c_int64, [c_desc_p]),
     "rnvp_grad_count": (C.c_int64, [c_desc_p]),
-    "rnvp_workspace_bytes": (C.c_int64, [c_desc_p]),
+    "rnvp_workspace_bytes": (C.c_int64, [c_desc_p, C.c_int64]),
     "rnvp_param_tensors": (C.c_int, [c_desc_p, C.POINTER(C.c_int64), C.c_int]),
     "rnvp_plan_info": (C.c_int, [c_desc_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]),

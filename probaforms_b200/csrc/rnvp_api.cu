@@ -59,6 +59,7 @@ struct rnvp_desc : rnvp_planner::FlowGeom {
   int* d_f2p = nullptr;   // flat index -> packed index or -1
   int* d_f2p2 = nullptr;  // flat index -> index in the small-flow layout or -1 (nullptr if unused)
   int* d_m2f = nullptr;   // tcgen05 region: 4*flat + code (0 hi, 1 lo, 2 full) or -1
+  int* d_f2m = nullptr;   // [2*P]: position of each parameter's TF32 hi / lo image in the tcgen05 region, or -1
   int path = 0;           // 0 auto, 1 FP32 tile/small kernels only, 2 tcgen05 where eligible
   std::map<std::tuple<int, int, int>, Program> programs;
   std::mutex mu;
@@ -144,8 +145,8 @@ __global__ void unpack_kernel(const float* __restrict__ gpacked, float* __restri
 // packed parameter copy, the re-zeroing of the accumulator and the hand-off of the step's loss.
 __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packed, float* __restrict__ gpacked,
                             const float* __restrict__ gflat_in, float* __restrict__ m, float* __restrict__ v,
-                            float* __restrict__ gflat_out, const int* __restrict__ f2p, const int* __restrict__ f2p2, int n,
-                            float grad_scale,
+                            float* __restrict__ gflat_out, const int* __restrict__ f2p, const int* __restrict__ f2p2,
+                            const int* __restrict__ f2m, float* __restrict__ mma_img, int n, float grad_scale,
                             float wd, float one_minus_b1, float b2, float one_minus_b2, float step_size,
                             float bc2_sqrt, float eps, int zero_gpacked, float* loss_src, float* loss_dst,
                             float loss_scale) {
@@ -175,6 +176,12 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packe
   if (f2p2) {
     const int p2 = f2p2[i];
     if (p2 >= 0) packed[p2] = th;
+  }
+  if (f2m) {                                           // TF32 hi / lo images of the tcgen05 kernels (see tc05.cuh)
+    const int mh = f2m[2 * i], ml = f2m[2 * i + 1];
+    const uint32_t h = (__float_as_uint(th) + 0x1000u) & 0xFFFFE000u;
+    if (mh >= 0) mma_img[mh] = __uint_as_float(h);
+    if (ml >= 0) mma_img[ml] = __uint_as_float((__float_as_uint(th - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u);
   }
 }
 
@@ -233,7 +240,8 @@ int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const
 bool use_mma(const rnvp_desc* d) { return d->mma_ok && d->path != 1; }
 
 int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
-            const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream) {
+            const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream,
+            float* stash = nullptr, float* loss_sum = nullptr) {
   if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
   if (N <= 0) return 0;
   RnvpMmaArgs a;
@@ -242,6 +250,7 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.out_x = out_x; a.out_logdet = out_logdet; a.out_logp = out_logp;
   a.Cd = d->Cd; a.H = d->hidden[0]; a.l0 = l0; a.l1 = l1;
   a.layer_floats = d->m_layer_floats; a.w1_floats = d->m_w1_floats; a.w2_floats = d->m_w2_floats;
+  a.stash = stash; a.loss_sum = loss_sum; a.L_total = d->L;
   const long long pairs = (N + 255) / 256;
   if (pairs > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
   a.n_pairs = (int)pairs;
@@ -297,8 +306,13 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
   if (d->mma_ok) {
     std::vector<int> m2f;
     build_mma_map(d, m2f);
+    std::vector<int> f2m(2 * (size_t)d->P, -1);
+    for (size_t m = 0; m < m2f.size(); ++m)
+      if (m2f[m] >= 0 && (m2f[m] & 3) < 2) f2m[2 * (size_t)(m2f[m] >> 2) + (m2f[m] & 3)] = (int)m;
     e = cudaMalloc(&d->d_m2f, sizeof(int) * m2f.size());
     if (e == cudaSuccess) e = cudaMemcpy(d->d_m2f, m2f.data(), sizeof(int) * m2f.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_f2m, sizeof(int) * f2m.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_f2m, f2m.data(), sizeof(int) * f2m.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
   }
   e = cudaMalloc(&d->d_p2f, sizeof(int) * p2f.size());
@@ -320,6 +334,7 @@ void rnvp_desc_destroy(rnvp_desc* d) {
   cudaFree(d->d_f2p);
   cudaFree(d->d_f2p2);
   cudaFree(d->d_m2f);
+  cudaFree(d->d_f2m);
   delete d;
 }
 
@@ -327,9 +342,10 @@ int64_t rnvp_param_count(const rnvp_desc* d) { return d ? d->P : -1; }
 int64_t rnvp_packed_count(const rnvp_desc* d) { return d ? d->packed : -1; }
 int64_t rnvp_grad_count(const rnvp_desc* d) { return d ? d->packed_tile : -1; }
 
-int64_t rnvp_workspace_bytes(const rnvp_desc* dc) {
+int64_t rnvp_workspace_bytes(const rnvp_desc* dc, int64_t N) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
   if (!d) return -1;
+  if (use_mma(d)) return std::max<int64_t>(N, 1) * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
   Program* p = nullptr;
   if (get_program(d, 2, 0, d->L, &p)) return -1;
   return (int64_t)p->stash_per_cta * 4 * d->num_sms * p->occupancy;
@@ -354,14 +370,14 @@ int rnvp_param_tensors(const rnvp_desc* d, int64_t* offsets, int max_tensors) {
 int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_bytes, int* n_ops, int* kernel_family) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
   if (check_desc(d)) return RNVP_EINVAL;
-  if (mode < 0 || mode > 2) return fail(RNVP_EINVAL, "mode must be 0, 1 or 2");
+  if (mode < 0 || mode > 3) return fail(RNVP_EINVAL, "mode must be 0..3");
   Program* p = nullptr;
   int rc = get_program(d, mode, 0, d->L, &p);
   if (rc) return rc;
   if (tile_rows) *tile_rows = 8 * p->TR;
   if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
   if (n_ops) *n_ops = p->n_ops;
-  if (kernel_family) *kernel_family = mode == 2 ? 0 : (use_mma(d) ? 2 : (d->small_ok ? 1 : 0));
+  if (kernel_family) *kernel_family = use_mma(d) ? 2 : ((mode < 2 && d->small_ok) ? 1 : 0);
   return 0;
 }
 
@@ -434,8 +450,24 @@ int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, 
   if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_backward: C must be given iff cond_size > 0");
   RnvpKArgs a;
   memset(&a, 0, sizeof(a));
-  a.packed = d_packed; a.X = d_X; a.C = d_C; a.idx = (const long long*)d_idx; a.N = N;
-  a.out_logp = d_logp; a.gpacked = d_gpacked; a.loss_sum = d_logp_sum; a.scale = scale;
+  a.packed = d_packed; a.C = d_C; a.idx = (const long long*)d_idx; a.N = N;
+  a.gpacked = d_gpacked; a.scale = scale;
+  if (use_mma(d) && N > 0) {
+    // forward sweep on the tensor cores (z, per-layer x_T and s to the workspace), backward sweep on the FP32 tile kernel
+    const int64_t need = (int64_t)N * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
+    if (!d_workspace || workspace_bytes < need)
+      return fail(RNVP_EINVAL, "rnvp_backward: workspace too small (see rnvp_workspace_bytes)");
+    float* z = (float*)d_workspace;
+    float* stash = z + (size_t)N * d->D;
+    int rc = run_mma(d, 2, 0, d->L, d_packed, d_X, d_C, (const long long*)d_idx, N, z, nullptr, d_logp,
+                     (cudaStream_t)stream, stash, d_logp_sum);
+    if (rc) return rc;
+    a.X = z;
+    a.gstash = stash; a.gstash_row = d->L * 2 * d->mDH; a.gstash_half = d->mDH;
+    return run_tile(d, 3, 0, d->L, a, nullptr, 0, (cudaStream_t)stream);
+  }
+  a.X = d_X;
+  a.out_logp = d_logp; a.loss_sum = d_logp_sum;
   return run_tile(d, 2, 0, d->L, a, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -454,8 +486,8 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
   const float bc2_sqrt = (float)sqrt(bc2);
   const int n = (int)d->P;
   adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      d_flat, d_packed, d_gpacked, d_gflat_in, d_exp_avg, d_exp_avg_sq, d_gflat_out, d->d_f2p, d->d_f2p2, n,
-      grad_scale,
+      d_flat, d_packed, d_gpacked, d_gflat_in, d_exp_avg, d_exp_avg_sq, d_gflat_out, d->d_f2p, d->d_f2p2,
+      d->mma_ok ? d->d_f2m : nullptr, d_packed + d->mma_off, n, grad_scale,
       (float)weight_decay, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), step_size, bc2_sqrt, (float)eps,
       zero_gpacked, d_loss_src, d_loss_dst, loss_scale);
   cudaError_t e = cudaGetLastError();

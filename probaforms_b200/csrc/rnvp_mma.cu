@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
       const uint32_t w2_bytes = (uint32_t)a.w2_floats * 4u;
       for (int it = 0; it < my_pairs; ++it)
         for (int li = 0; li < nL; ++li, ++step) {
-          const int i = MODE == 0 ? a.l0 + li : a.l1 - 1 - li;
+          const int i = MODE != 1 ? a.l0 + li : a.l1 - 1 - li;
           const float* src = a.wimg + (size_t)i * a.layer_floats;
           if (step > 0) { mbar_wait(&bars[B_W1E], ph1); ph1 ^= 1; }
           mbar_expect_tx(&bars[B_W1F], w1_bytes);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
         tmem_st_x8(trow + U_LO + DH + e0, lo);
       }
 
-      auto layer = [&](float (&xT)[DH], float (&xK)[DH], int li) {
+      auto layer = [&](float (&xT)[DH], float (&xK)[DH], int i) {
         // ---- u (conditioning half) -> TMEM
 #pragma unroll
         for (int e0 = 0; e0 < DH; e0 += 8) {
@@ -397,15 +397,26 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             if (NETSEQ) t = tpark[NETSEQ ? e0 + j : 0];
             else t = USE_C2 ? __uint_as_float(tv[j]) + __uint_as_float(tc[j]) : __uint_as_float(tv[j]);
             const float s = USE_C2 ? __uint_as_float(sv[j]) + __uint_as_float(sc[j]) : __uint_as_float(sv[j]);
-            if (MODE == 0) { xT[e0 + j] = fmaf(xT[e0 + j], expf(s), t); ld += s; }
+            if (MODE == 2) { sv[j] = __float_as_uint(s); tv[j] = __float_as_uint(xT[e0 + j]); }   // stash s and x_T
+            if (MODE != 1) { xT[e0 + j] = fmaf(xT[e0 + j], expf(s), t); ld += s; }
             else xT[e0 + j] = (xT[e0 + j] - t) * expf(-s);
+          }
+          if (MODE == 2 && valid) {
+            float4* sp = reinterpret_cast<float4*>(a.stash + ((size_t)row * a.L_total + i) * (2 * DH) + e0);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              sp[m] = make_float4(__uint_as_float(tv[4 * m]), __uint_as_float(tv[4 * m + 1]), __uint_as_float(tv[4 * m + 2]),
+                                  __uint_as_float(tv[4 * m + 3]));
+              sp[DH / 4 + m] = make_float4(__uint_as_float(sv[4 * m]), __uint_as_float(sv[4 * m + 1]),
+                                           __uint_as_float(sv[4 * m + 2]), __uint_as_float(sv[4 * m + 3]));
+            }
           }
         }
       };
       for (int li = 0; li < nL; ++li) {
-        const int i = MODE == 0 ? a.l0 + li : a.l1 - 1 - li;
-        if ((i & 1) == 0) layer(xa, xb, li);             // even layer transforms the even features
-        else layer(xb, xa, li);
+        const int i = MODE != 1 ? a.l0 + li : a.l1 - 1 - li;
+        if ((i & 1) == 0) layer(xa, xb, i);              // even layer transforms the even features
+        else layer(xb, xa, i);
       }
 
       if (valid) {
@@ -414,12 +425,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
           for (int m = 0; m < DH / 2; ++m)
             reinterpret_cast<float4*>(a.out_x + row * D)[m] = make_float4(xa[2 * m], xb[2 * m], xa[2 * m + 1], xb[2 * m + 1]);
         }
-        if (MODE == 0) {
-          float q = 0.0f;
+      }
+      if (MODE != 1) {
+        float q = 0.0f;
 #pragma unroll
-          for (int e = 0; e < DH; ++e) { q = fmaf(xa[e], xa[e], q); q = fmaf(xb[e], xb[e], q); }
+        for (int e = 0; e < DH; ++e) { q = fmaf(xa[e], xa[e], q); q = fmaf(xb[e], xb[e], q); }
+        float lp = valid ? ld - 0.5f * (D * 1.8378770664093453f + q) : 0.0f;
+        if (valid) {
           if (a.out_logdet) a.out_logdet[row] = ld;
-          if (a.out_logp) a.out_logp[row] = ld - 0.5f * (D * 1.8378770664093453f + q);
+          if (a.out_logp) a.out_logp[row] = lp;
+        }
+        if (MODE == 2 && a.loss_sum) {
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, m);
+          if (lane == 0) atomicAdd(a.loss_sum, lp);
         }
       }
     }
@@ -441,8 +460,10 @@ cudaError_t launch_mma_shape(int act, int mode, const RnvpMmaArgs& a, int grid, 
   }
   if (act == 1 && mode == 0) RNVP_MMA_LAUNCH(1, 0)
   if (act == 1 && mode == 1) RNVP_MMA_LAUNCH(1, 1)
+  if (act == 1 && mode == 2) RNVP_MMA_LAUNCH(1, 2)
   if (act == 2 && mode == 0) RNVP_MMA_LAUNCH(2, 0)
   if (act == 2 && mode == 1) RNVP_MMA_LAUNCH(2, 1)
+  if (act == 2 && mode == 2) RNVP_MMA_LAUNCH(2, 2)
 #undef RNVP_MMA_LAUNCH
   return cudaErrorInvalidValue;
 }

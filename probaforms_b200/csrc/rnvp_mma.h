@@ -14,4 +14,9 @@ struct RnvpMmaArgs {
   int Cd, H, l0, l1;
   int layer_floats, w1_floats, w2_floats;
   int n_pairs;                 // pairs of 128-row tiles
+  // MODE 2 (forward pass of a fit step): per layer the row's x_T (before the coupling) and s go to a global stash,
+  // [row][layer][x_T(DH) | s(DH)], read back by the backward-only tile program; sum of logp accumulates atomically
+  float* stash;
+  float* loss_sum;
+  int L_total;                 // layers of the flow (stash row = L_total * 2 * DH floats)
 };

@@ -36,7 +36,9 @@ enum RnvpOpFlags {
   F_FIRST = 8,        // DGRAD: first chunk of the reduction
   F_LAST = 16,        // DGRAD: last chunk of the reduction
   F_TO_GU = 32,       // DGRAD: q = 0, result is du (input gradient), no act'
-  F_NET_S_ONLY = 64   // LINEAR: only nn_s needs this output (t is unused in the backward sweep)
+  F_NET_S_ONLY = 64,  // LINEAR: only nn_s needs this output (t is unused in the backward sweep)
+  F_GSTASH = 128      // backward-only program: x_T and s come from the row-major global stash written by the
+                      // tcgen05 forward kernel ([row][layer][x_T(|T|max) | s(|T|max)]); LOAD: X rows are not gathered
 };
 
 struct RnvpOp {
@@ -93,6 +95,8 @@ struct RnvpKArgs {
   float* loss_sum;                    // sum over rows of logp (backward), atomically accumulated
   float* stash;                       // per-CTA x_T stash, gridDim.x * stash_per_cta floats
   int stash_per_cta;
+  const float* gstash;                // backward-only program: global stash of the forward kernel
+  int gstash_row, gstash_half;        // floats per row (L*2*half) and per half (|T|max)
   float scale;                        // backward: d(out)/d(logp_row); g_logdet = scale, g_z = -z*scale
   int D, Cd;
   RnvpSmem sm;

@@ -339,7 +339,7 @@ struct Builder {
     sm.xs = take(R * sm.xs_stride);
     sm.cs_stride = pad_stride(std::max(Cd, 1));
     sm.cs = take(Cd > 0 ? R * sm.cs_stride : 4);
-    sm.gx = mode == 2 ? take(R * sm.xs_stride) : 0;
+    sm.gx = mode >= 2 ? take(R * sm.xs_stride) : 0;
     sm.ub_stride = pad_stride(std::max(maxK1c, 1));
     sm.ub = take(R * sm.ub_stride);
     sm.ld = take(R);
@@ -348,10 +348,10 @@ struct Builder {
     sm.st = take(2 * sm.st_net);
     sm.gu_stride = pad_stride(std::max(maxK, 1));
     sm.gu_net = R * sm.gu_stride;
-    sm.gu = mode == 2 ? take(2 * sm.gu_net) : 0;
+    sm.gu = mode >= 2 ? take(2 * sm.gu_net) : 0;
     hbuf_off.clear();
     hbuf_stride.clear();
-    if (mode == 2) {
+    if (mode >= 2) {
       bool chunked = false;
       for (int q = 0; q < nh; ++q) {
         hbuf_stride.push_back(pad_stride(d->hidden[q]));
@@ -411,7 +411,7 @@ struct Builder {
   }
 
   void hidden_buffer(int q, int* off, int* stride) const {
-    const int b = mode == 2 ? q : (q & 1) % (int)hbuf_off.size();
+    const int b = mode >= 2 ? q : (q & 1) % (int)hbuf_off.size();
     *off = hbuf_off[b];
     *stride = hbuf_stride[b];
   }
@@ -520,7 +520,12 @@ struct Builder {
     for (int i = l0; i < l1; ++i) { stash_off[i] = stash_per_cta; stash_per_cta += R * d->layers[i].nT; }
     stash_per_cta = ceil4(std::max(stash_per_cta, 4));
 
-    ops.push_back(base_op(OP_LOAD, -1));
+    {
+      RnvpOp ld = base_op(OP_LOAD, -1);
+      if (mode == 3) ld.flags = F_GSTASH;
+      ops.push_back(ld);
+    }
+    if (mode == 3) ops.push_back(base_op(OP_SEED_B, -1));
     if (mode == 0 || mode == 2) {
       for (int i = l0; i < l1; ++i)
         if (d->layers[i].nT > 0) emit_forward_layer(i, mode == 2);
@@ -537,19 +542,25 @@ struct Builder {
       }
       ops.push_back(base_op(OP_STORE_G, -1));
     }
-    if (mode == 2) {
+    if (mode >= 2) {
+      // mode 3 = backward sweep only: z, x_T and s of every layer were left in global memory by the tcgen05
+      // forward kernel, so the forward sweep and the recomputation of s are skipped
       int prev_with_gu = -1;
       for (int i = l1 - 1; i >= l0; --i) {
         const LayerGeom& lg = d->layers[i];
         if (lg.nT == 0) continue;
         RnvpOp b = base_op(OP_BUILD_U, i);
-        b.flags = F_RESTORE;
+        b.flags = F_RESTORE | (mode == 3 ? F_GSTASH : 0);
         b.stash_off = stash_off[i];
         if (prev_with_gu == i + 1) b.flags |= F_ADDGU;
         ops.push_back(b);
         for (int q = 0; q < nh; ++q) emit_linear(i, q, 0);
-        emit_linear(i, nh, F_NET_S_ONLY);
-        ops.push_back(base_op(OP_COUPLE_B, i));
+        if (mode == 2) emit_linear(i, nh, F_NET_S_ONLY);
+        {
+          RnvpOp cb = base_op(OP_COUPLE_B, i);
+          if (mode == 3) cb.flags = F_GSTASH;
+          ops.push_back(cb);
+        }
         for (int q = nh; q >= 0; --q) {
           emit_wgrad(i, q);
           if (q > 0) emit_dgrad(i, q, false);

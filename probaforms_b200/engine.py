@@ -64,6 +64,7 @@ class FlowEngine:
         self.adam_steps = 0
         self._workspace = None
         self.launches = 0                                 # kernels launched through this engine
+        self._bwd_two_kernels = self.plan_info(2)["kernel_family"] == 2
 
     def __del__(self):
         try:
@@ -106,14 +107,17 @@ class FlowEngine:
     def set_path(self, path):
         """0 auto (tcgen05 TF32x3 kernels where eligible), 1 FP32-FMA kernels only."""
         _lib.check(self.lib.rnvp_set_path(self._desc, int(path)), "rnvp_set_path")
+        self._workspace = None
+        self._bwd_two_kernels = self.plan_info(2)["kernel_family"] == 2
 
-    def workspace(self):
-        if self._workspace is None:
-            with torch.cuda.device(self.device):
-                nbytes = int(self.lib.rnvp_workspace_bytes(self._desc))
-            if nbytes < 0:
-                _lib.check(-1, "rnvp_workspace_bytes")
-            self._workspace = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=self.device)
+    def workspace(self, n_rows=1):
+        """Scratch for rnvp_backward on a batch of ``n_rows`` rows (grown on demand, never shrunk)."""
+        with torch.cuda.device(self.device):
+            nbytes = int(self.lib.rnvp_workspace_bytes(self._desc, int(n_rows)))
+        if nbytes < 0:
+            _lib.check(-1, "rnvp_workspace_bytes")
+        if self._workspace is None or self._workspace.numel() * 4 < nbytes:
+            self._workspace = torch.empty(max(nbytes, 16) // 4 + 4, dtype=torch.float32, device=self.device)
         return self._workspace
 
     # ------------------------------------------------------------------ kernels
@@ -163,13 +167,14 @@ class FlowEngine:
         """Fused forward+backward of scale*sum_rows logp; ACCUMULATES into gpacked / loss_slot."""
         if n_rows <= 0:
             return
-        ws = self.workspace()
+        ws = self.workspace(n_rows)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.rnvp_backward(self._desc, _ptr(self.packed), _ptr(X), _ptr(Cn), _ptr(idx), n_rows,
                                               C.c_float(scale), _ptr(self.gpacked), _ptr(self.loss_slot),
                                               _ptr(logp_rows), _ptr(ws), ws.numel() * 4, self._stream()),
                        "rnvp_backward")
-        self.launches += 1
+        # tcgen05 path: tensor-core forward sweep + FP32 backward-only sweep = two kernels
+        self.launches += 2 if self._bwd_two_kernels else 1
 
     def unpack_grads(self, out=None):
         """Packed accumulator -> reference-layout flat gradient (exact zeros on masked entries)."""

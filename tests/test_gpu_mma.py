@@ -63,3 +63,29 @@ def test_tcgen05_flow_matches_fp32_kernels(shape, N):
     assert rel(z, z0) < 1e-5 and rel(lp, lp0) < 1e-5 and rel(ld, ld0) < 1e-5
     assert rel(xs, xs0) < 1e-5
     assert float((x_back - X).abs().max()) < 1e-4 * max(1.0, float(X.abs().max()))
+
+
+def test_fit_steps_on_tcgen05_path_track_fp32_path():
+    """Regression: the Adam kernel must refresh the TF32 hi/lo weight images of the tcgen05 kernels every step
+    (a stale image trains nothing).  20 fused fit steps on both kernel families give the same loss curve."""
+    from probaforms_b200.models import RealNVPLayer, NormalizingFlow
+    dev = torch.device("cuda:0")
+    D, Cd, L, H, N = 32, 8, 6, 64, 4096
+    curves = {}
+    for path in (1, 0):
+        torch.manual_seed(0)
+        nf = NormalizingFlow([RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, (H,), "tanh") for i in range(L)], None).to(dev)
+        eng = nf._fused()
+        eng.set_path(path)
+        assert eng.plan_info(2)["kernel_family"] == (2 if path == 0 else 0)
+        g = torch.Generator(device=dev).manual_seed(1)
+        X = torch.randn(4 * N, D, device=dev, generator=g)
+        C = torch.randn(4 * N, Cd, device=dev, generator=g)
+        perm = torch.randint(0, 4 * N, (20 * N,), device=dev, generator=g)
+        losses = torch.zeros(20, device=dev)
+        eng.zero_grads()
+        for s in range(20):
+            eng.fit_step(X, C, perm[s * N:(s + 1) * N], N, N, 1e-3, 0.0, losses[s:s + 1])
+        curves[path] = losses.cpu()
+    assert float(curves[1][-1]) < float(curves[1][0]) - 1.0          # it does train
+    assert torch.allclose(curves[0], curves[1], rtol=1e-4, atol=1e-4), (curves[0], curves[1])
