@@ -109,6 +109,14 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
                    double weight_decay, int64_t step, int zero_gpacked, float* d_loss_src,
                    float* d_loss_dst, float loss_scale, void* stream);
 
+/* Weight-gradient sweep from stored activations (last part of a fit step on the tcgen05 path): for every layer
+ * dW1 += delta1^T u, db1 += sum delta1, dW2 += delta2^T h, db2 += sum delta2 (sums over rows), accumulated into
+ * d_gpacked.  d_records is [L][Npad][rec] with rec = rnvp_wgrad_record_floats(d) and one record per (layer, row):
+ * delta1 [2][H] (nn_t | nn_s) | h [2][H] | u = [x_K, c, 0..] (ceil8(D/2+Cd)) | delta2 [2][D/2] | padding.
+ * Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.  tcgen05-eligible flows, H <= 128. */
+int rnvp_wgrad_record_floats(const rnvp_desc* d);
+int rnvp_wgrad_sweep(const rnvp_desc* d, int64_t Npad, const float* d_records, float* d_gpacked, void* stream);
+
 /* Kernel-family selection for rnvp_forward / rnvp_inverse: 0 = auto (tcgen05 TF32x3 kernels where the shape is
  * eligible -- one hidden layer, D/2 in {16,32} --, else the small-flow or FP32 tile kernels), 1 = FP32-FMA kernels
  * only, 2 = same as auto.  rnvp_plan_info reports the family chosen (0 tile, 1 small-flow, 2 tcgen05). */

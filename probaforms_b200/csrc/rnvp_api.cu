@@ -18,6 +18,7 @@
 #include "rnvp_planner.h"
 #include "rnvp_small.h"
 #include "rnvp_mma.h"
+#include "rnvp_wgrad.h"
 
 cudaError_t rnvp_launch_tile(int mode, int TR, const RnvpKArgs& a, int grid, size_t smem_bytes, cudaStream_t stream);
 int rnvp_tile_occupancy(int mode, int TR, size_t smem_bytes);
@@ -25,7 +26,9 @@ cudaError_t rnvp_launch_small(int NE, int NC, int act, int mode, const RnvpSmall
                               cudaStream_t st);
 int rnvp_small_rows_per_block();
 cudaError_t rnvp_launch_mma(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st);
-size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats);
+size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats, int w1t_floats);
+cudaError_t rnvp_launch_wgrad(int NT1, int NT2, const RnvpWgradArgs& a, int grid, size_t smem, cudaStream_t st);
+size_t rnvp_wgrad_smem_bytes(int rec, int bw);
 cudaError_t rnvp_launch_mma_selftest(const float* A, const float* B, float* D, int N, int K, int passes, cudaStream_t st);
 
 namespace {
@@ -59,7 +62,8 @@ struct rnvp_desc : rnvp_planner::FlowGeom {
   int* d_f2p = nullptr;   // flat index -> packed index or -1
   int* d_f2p2 = nullptr;  // flat index -> index in the small-flow layout or -1 (nullptr if unused)
   int* d_m2f = nullptr;   // tcgen05 region: 4*flat + code (0 hi, 1 lo, 2 full) or -1
-  int* d_f2m = nullptr;   // [2*P]: position of each parameter's TF32 hi / lo image in the tcgen05 region, or -1
+  int* d_f2m = nullptr;   // [4*P]: positions of each parameter's TF32 hi / lo images (plain, transposed) in the tcgen05 region, or -1
+  RnvpWgradLayer* d_wg = nullptr;   // per-layer gradient offsets for the weight-gradient sweep
   int path = 0;           // 0 auto, 1 FP32 tile/small kernels only, 2 tcgen05 where eligible
   std::map<std::tuple<int, int, int>, Program> programs;
   std::mutex mu;
@@ -178,10 +182,13 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packe
     if (p2 >= 0) packed[p2] = th;
   }
   if (f2m) {                                           // TF32 hi / lo images of the tcgen05 kernels (see tc05.cuh)
-    const int mh = f2m[2 * i], ml = f2m[2 * i + 1];
+    const int4 mm = reinterpret_cast<const int4*>(f2m)[i];
     const uint32_t h = (__float_as_uint(th) + 0x1000u) & 0xFFFFE000u;
-    if (mh >= 0) mma_img[mh] = __uint_as_float(h);
-    if (ml >= 0) mma_img[ml] = __uint_as_float((__float_as_uint(th - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u);
+    const float fh = __uint_as_float(h), fl = __uint_as_float((__float_as_uint(th - fh) + 0x1000u) & 0xFFFFE000u);
+    if (mm.x >= 0) mma_img[mm.x] = fh;
+    if (mm.y >= 0) mma_img[mm.y] = fl;
+    if (mm.z >= 0) mma_img[mm.z] = fh;
+    if (mm.w >= 0) mma_img[mm.w] = fl;
   }
 }
 
@@ -238,10 +245,18 @@ int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const
 }
 
 bool use_mma(const rnvp_desc* d) { return d->mma_ok && d->path != 1; }
+// fit step entirely on the tensor-core path (tcgen05 forward + backward sweeps, mma.sync weight-gradient sweep)
+bool use_mma_bwd(const rnvp_desc* d) { return use_mma(d) && d->m_wt_floats > 0; }
+// record stride of the activation records exchanged between the backward sweep and the weight-gradient sweep
+int wgrad_rec_floats(const rnvp_desc* d) {
+  const int K1P = (d->mDH + d->Cd + 7) & ~7;
+  const int n = 4 * d->hidden[0] + K1P + 2 * d->mDH;
+  return ((n + 31) & ~31) + 8;
+}
 
 int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
             const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream,
-            float* stash = nullptr, float* loss_sum = nullptr) {
+            float* stash = nullptr, float* loss_sum = nullptr, float* records = nullptr, float scale = 0.f) {
   if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
   if (N <= 0) return 0;
   RnvpMmaArgs a;
@@ -251,11 +266,14 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.Cd = d->Cd; a.H = d->hidden[0]; a.l0 = l0; a.l1 = l1;
   a.layer_floats = d->m_layer_floats; a.w1_floats = d->m_w1_floats; a.w2_floats = d->m_w2_floats;
   a.stash = stash; a.loss_sum = loss_sum; a.L_total = d->L;
+  a.do_bwd = records != nullptr; a.scale = scale; a.records = records; a.rec = 0; a.Npad = 0;
+  a.wt_floats = records ? d->m_wt_floats : 0;
   const long long pairs = (N + 255) / 256;
   if (pairs > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
   a.n_pairs = (int)pairs;
+  if (records) { a.rec = wgrad_rec_floats(d); a.Npad = pairs * 256; }
   const int grid = (int)std::min<long long>(pairs, d->num_sms);
-  cudaError_t e = rnvp_launch_mma(d->mDH, d->act, mode, a, grid, rnvp_mma_smem_bytes(d->m_w1_floats, d->m_w2_floats), stream);
+  cudaError_t e = rnvp_launch_mma(d->mDH, d->act, mode, a, grid, rnvp_mma_smem_bytes(d->m_w1_floats, d->m_w2_floats, a.wt_floats), stream);
   if (e != cudaSuccess) return cuda_fail(e, "tcgen05 kernel launch");
   return 0;
 }
@@ -306,13 +324,32 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
   if (d->mma_ok) {
     std::vector<int> m2f;
     build_mma_map(d, m2f);
-    std::vector<int> f2m(2 * (size_t)d->P, -1);
+    std::vector<int> f2m(4 * (size_t)d->P, -1);       // per parameter: hi, lo, hi (transposed image), lo (transposed image)
     for (size_t m = 0; m < m2f.size(); ++m)
-      if (m2f[m] >= 0 && (m2f[m] & 3) < 2) f2m[2 * (size_t)(m2f[m] >> 2) + (m2f[m] & 3)] = (int)m;
+      if (m2f[m] >= 0 && (m2f[m] & 3) < 2) {
+        int* slot = &f2m[4 * (size_t)(m2f[m] >> 2) + (m2f[m] & 3)];
+        if (*slot >= 0) slot += 2;
+        *slot = (int)m;
+      }
     e = cudaMalloc(&d->d_m2f, sizeof(int) * m2f.size());
     if (e == cudaSuccess) e = cudaMemcpy(d->d_m2f, m2f.data(), sizeof(int) * m2f.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&d->d_f2m, sizeof(int) * f2m.size());
     if (e == cudaSuccess) e = cudaMemcpy(d->d_f2m, f2m.data(), sizeof(int) * f2m.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
+  }
+  if (d->nh == 1) {
+    std::vector<RnvpWgradLayer> wl(d->L);
+    for (int i = 0; i < d->L; ++i) {
+      const LinearGeom& g0 = d->layers[i].lin[0];
+      const LinearGeom& g1 = d->layers[i].lin[1];
+      for (int net = 0; net < 2; ++net) {
+        wl[i].w1_off[net] = g0.w_off[net]; wl[i].b1_off[net] = g0.b_off[net];
+        wl[i].w2_off[net] = g1.w_off[net]; wl[i].b2_off[net] = g1.b_off[net];
+      }
+      wl[i].Ks1 = g0.Ks; wl[i].Ks2 = g1.Ks;
+    }
+    e = cudaMalloc(&d->d_wg, sizeof(RnvpWgradLayer) * wl.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_wg, wl.data(), sizeof(RnvpWgradLayer) * wl.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
   }
   e = cudaMalloc(&d->d_p2f, sizeof(int) * p2f.size());
@@ -335,6 +372,7 @@ void rnvp_desc_destroy(rnvp_desc* d) {
   cudaFree(d->d_f2p2);
   cudaFree(d->d_m2f);
   cudaFree(d->d_f2m);
+  cudaFree(d->d_wg);
   delete d;
 }
 
@@ -345,6 +383,10 @@ int64_t rnvp_grad_count(const rnvp_desc* d) { return d ? d->packed_tile : -1; }
 int64_t rnvp_workspace_bytes(const rnvp_desc* dc, int64_t N) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
   if (!d) return -1;
+  if (use_mma_bwd(d)) {
+    const int64_t n = std::max<int64_t>(N, 1), npad = (n + 255) / 256 * 256;
+    return (n * d->L * 2 * d->mDH + (int64_t)d->L * npad * wgrad_rec_floats(d)) * 4;
+  }
   if (use_mma(d)) return std::max<int64_t>(N, 1) * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
   Program* p = nullptr;
   if (get_program(d, 2, 0, d->L, &p)) return -1;
@@ -370,7 +412,7 @@ int rnvp_param_tensors(const rnvp_desc* d, int64_t* offsets, int max_tensors) {
 int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_bytes, int* n_ops, int* kernel_family) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
   if (check_desc(d)) return RNVP_EINVAL;
-  if (mode < 0 || mode > 3) return fail(RNVP_EINVAL, "mode must be 0..3");
+  if (mode < 0 || mode > 4) return fail(RNVP_EINVAL, "mode must be 0..4");
   Program* p = nullptr;
   int rc = get_program(d, mode, 0, d->L, &p);
   if (rc) return rc;
@@ -452,6 +494,19 @@ int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, 
   memset(&a, 0, sizeof(a));
   a.packed = d_packed; a.C = d_C; a.idx = (const long long*)d_idx; a.N = N;
   a.gpacked = d_gpacked; a.scale = scale;
+  if (use_mma_bwd(d) && N > 0) {
+    // forward + backward sweeps in one tcgen05 launch (per-layer records to the workspace), then the weight-gradient sweep
+    const int64_t npad = (N + 255) / 256 * 256;
+    const int64_t stash_f = (int64_t)N * d->L * 2 * d->mDH, rec_f = (int64_t)d->L * npad * wgrad_rec_floats(d);
+    if (!d_workspace || workspace_bytes < (stash_f + rec_f) * 4)
+      return fail(RNVP_EINVAL, "rnvp_backward: workspace too small (see rnvp_workspace_bytes)");
+    float* stash = (float*)d_workspace;
+    float* records = stash + stash_f;
+    int rc = run_mma(d, 2, 0, d->L, d_packed, d_X, d_C, (const long long*)d_idx, N, nullptr, nullptr, d_logp,
+                     (cudaStream_t)stream, stash, d_logp_sum, records, scale);
+    if (rc) return rc;
+    return rnvp_wgrad_sweep(d, npad, records, d_gpacked, stream);
+  }
   if (use_mma(d) && N > 0) {
     // forward sweep on the tensor cores (z, per-layer x_T and s to the workspace), backward sweep on the FP32 tile kernel
     const int64_t need = (int64_t)N * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
@@ -494,6 +549,28 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
   return e == cudaSuccess ? 0 : cuda_fail(e, "adam_kernel");
 }
 
+int rnvp_wgrad_record_floats(const rnvp_desc* d) {
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (!d->mma_ok) return fail(RNVP_ESHAPE, "rnvp_wgrad_record_floats: not a tcgen05-eligible flow");
+  return wgrad_rec_floats(d);
+}
+
+int rnvp_wgrad_sweep(const rnvp_desc* dc, int64_t Npad, const float* d_records, float* d_gpacked, void* stream) {
+  rnvp_desc* d = const_cast<rnvp_desc*>(dc);
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (!d->mma_ok || 2 * d->hidden[0] > 256 || d->hidden[0] % 16)
+    return fail(RNVP_ESHAPE, "rnvp_wgrad_sweep: needs a tcgen05-eligible flow with hidden width <= 128 (multiple of 16)");
+  if (!d_records || !d_gpacked) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: null buffer");
+  if (Npad <= 0 || Npad % 32) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: Npad must be a positive multiple of 32");
+  const int K1P = (d->mDH + d->Cd + 7) & ~7, TP = d->mDH;
+  RnvpWgradArgs a;
+  a.gR = d_records; a.rec = wgrad_rec_floats(d); a.gpacked = d_gpacked; a.layers = d->d_wg;
+  a.Npad = Npad; a.H = d->hidden[0];
+  a.n_slices = (int)std::max<long long>(1, std::min<long long>(Npad / 32, (d->num_sms + d->L - 1) / d->L));
+  cudaError_t e = rnvp_launch_wgrad(K1P / 8, TP / 8, a, d->L * a.n_slices, rnvp_wgrad_smem_bytes(a.rec, K1P + 2 * TP), (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "rnvp_wgrad_kernel");
+}
+
 int rnvp_set_path(rnvp_desc* d, int path) {
   if (check_desc(d)) return RNVP_EINVAL;
   if (path < 0 || path > 2) return fail(RNVP_EINVAL, "path must be 0 (auto), 1 (fp32 kernels) or 2 (tcgen05 where eligible)");
@@ -503,7 +580,7 @@ int rnvp_set_path(rnvp_desc* d, int path) {
 
 int rnvp_mma_selftest(const float* d_A, const float* d_B, float* d_D, int N, int K, int passes, void* stream) {
   if (!d_A || !d_B || !d_D) return fail(RNVP_EINVAL, "rnvp_mma_selftest: null buffer");
-  if (N < 16 || N > 256 || N % 16 || K < 8 || K > 64 || K % 8 || (passes != 1 && passes != 3))
+  if (N < 16 || N > 256 || N % 16 || K < 8 || K > 64 || K % 8 || (passes != 1 && passes != 3 && passes != 4 && passes != 5))
     return fail(RNVP_EINVAL, "rnvp_mma_selftest: need N%16==0 in [16,256], K%8==0 in [8,64], passes 1 or 3");
   cudaError_t e = rnvp_launch_mma_selftest(d_A, d_B, d_D, N, K, passes, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "mma_selftest_kernel");

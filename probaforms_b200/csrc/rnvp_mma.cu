@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
     const int n = e / K, k = e - n * K;
     uint32_t hi, lo;
     split_tf32(B[e], hi, lo);
-    Bhi[tiled_off(n, k, K)] = __uint_as_float(hi);
-    Blo[tiled_off(n, k, K)] = __uint_as_float(lo);
+    // passes 4 / 5: B stored MN-major (4 consecutive n contiguous, 8 k at 16 B stride, n-groups 128 B apart, k-groups after)
+    const int off = passes >= 4 ? (n & 3) + (k & 7) * 4 + (n >> 2) * 32 + (k >> 3) * (N >> 2) * 32 : tiled_off(n, k, K);
+    Bhi[off] = __uint_as_float(hi);
+    Blo[off] = __uint_as_float(lo);
   }
   // generic-proxy smem writes must be visible to the tensor core (async proxy)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -76,7 +78,16 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
     const uint32_t idesc = idesc_tf32(128, N);
     const uint32_t sbo = (uint32_t)(K >> 2) * 128u, lbo = 128u;
     uint32_t acc = 0;
-    for (int p = 0; p < passes; ++p) {
+    if (passes >= 4) {
+      // MN-major B: passes 4 = (LBO = k-group stride, SBO = n-group stride) as in the CUTLASS canonical form, 5 = swapped
+      const uint32_t kg = (uint32_t)(N >> 2) * 128u, ng = 128u;
+      for (int j = 0; j < K / 8; ++j) {
+        const uint64_t bdesc = smem_desc_kmajor_nosw(smem_u32(Bhi) + (uint32_t)j * kg, passes == 4 ? kg : ng, passes == 4 ? ng : kg);
+        mma_tf32_ts(tbase + colD, tbase + colA_hi + 8 * j, bdesc, idesc | (1u << 16), acc);
+        acc = 1;
+      }
+    }
+    for (int p = 0; p < (passes >= 4 ? 0 : passes); ++p) {
       const uint32_t a_col = (p == 1) ? colA_lo : colA_hi;
       const float* Bp = (p == 2) ? Blo : Bhi;
       for (int j = 0; j < K / 8; ++j) {
@@ -141,7 +152,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
   float* w2buf = sm + a.w1_floats;
   // w2buf also holds, after the W2 blocks, the b2 images: per net [hi | lo] of an [NTP x 8] operand whose only
   // non-zero column multiplies the constant-one column of u, so that GEMM2 starts from the bias
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w2buf + a.w2_floats);
+  float* w1tbuf = w2buf + a.w2_floats;                 // backward sweep only: W1T image (the W2T image reuses w2buf)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w1tbuf + a.wt_floats);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -173,17 +185,26 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
       long long step = 0;
       const uint32_t w1_bytes = (uint32_t)(4 * H * K1P) * 4u;          // actual image size for this Cd
       const uint32_t w2_bytes = (uint32_t)a.w2_floats * 4u;
+      const int n_sweeps = (MODE == 2 && !NETSEQ && a.do_bwd) ? 2 : 1;   // fit step: forward sweep, then backward sweep
       for (int it = 0; it < my_pairs; ++it)
-        for (int li = 0; li < nL; ++li, ++step) {
-          const int i = MODE != 1 ? a.l0 + li : a.l1 - 1 - li;
-          const float* src = a.wimg + (size_t)i * a.layer_floats;
-          if (step > 0) { mbar_wait(&bars[B_W1E], ph1); ph1 ^= 1; }
-          mbar_expect_tx(&bars[B_W1F], w1_bytes);
-          bulk_g2s(w1buf, src, w1_bytes, &bars[B_W1F]);
-          if (step > 0) { mbar_wait(&bars[B_W2E], ph2); ph2 ^= 1; }
-          mbar_expect_tx(&bars[B_W2F], w2_bytes);
-          bulk_g2s(w2buf, src + a.w1_floats, w2_bytes, &bars[B_W2F]);
-        }
+        for (int sw = 0; sw < n_sweeps; ++sw)
+          for (int li = 0; li < nL; ++li, ++step) {
+            const int i = (MODE == 1 || sw == 1) ? a.l1 - 1 - li : a.l0 + li;
+            const float* src = a.wimg + (size_t)i * a.layer_floats;
+            const uint32_t wt_bytes = (uint32_t)a.wt_floats * 4u;
+            if (step > 0) { mbar_wait(&bars[B_W1E], ph1); ph1 ^= 1; }
+            mbar_expect_tx(&bars[B_W1F], sw ? w1_bytes + wt_bytes : w1_bytes);
+            bulk_g2s(w1buf, src, w1_bytes, &bars[B_W1F]);
+            if (sw) bulk_g2s(w1tbuf, src + a.w1_floats + a.w2_floats + a.wt_floats, wt_bytes, &bars[B_W1F]);
+            if (step > 0) { mbar_wait(&bars[B_W2E], ph2); ph2 ^= 1; }
+            if (sw) {       // backward sweep: the W2T image takes the place of the W2 image
+              mbar_expect_tx(&bars[B_W2F], wt_bytes);
+              bulk_g2s(w2buf, src + a.w1_floats + a.w2_floats, wt_bytes, &bars[B_W2F]);
+            } else {
+              mbar_expect_tx(&bars[B_W2F], w2_bytes);
+              bulk_g2s(w2buf, src + a.w1_floats, w2_bytes, &bars[B_W2F]);
+            }
+          }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -245,7 +266,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                     tb + D1C + net * CU, tb + A_LO + net * CU);
       }
     };
-    for (int it = 0; it < my_pairs; ++it)
+    for (int it = 0; it < my_pairs; ++it) {
       for (int li = 0; li < nL; ++li) {
         mbar_wait(&bars[B_W1F], ph_w1); ph_w1 ^= 1;
         for (int g = 0; g < 2; ++g) {
@@ -276,6 +297,99 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             __syncwarp();
           }
       }
+      if constexpr (MODE == 2 && !NETSEQ) {
+        if (a.do_bwd) {
+          // ---------------- backward sweep: per half-chunk of 16 units per net
+          //   gemmA: D1B = u W1^T (recompute pre-activations)   and   DHB = delta2 W2   (dh)
+          //   gemmB: DU += delta1 W1[:, x_K columns]                                      (du)
+          // The transposed products read K-major images of W2^T (in w2buf during this sweep) and W1^T (w1tbuf): per
+          // (half-chunk, net) a [16 x 16] block [hi | lo].  (tf32 operands cannot be read MN-major without swizzle.)
+          constexpr int D1B = 2 * K1PMAX, DHB = D1B + 32, E2H = DHB + 32, E2L = E2H + 32, DUM = E2L + 32, DUC = DUM + 16;
+          static_assert(DUC + 16 <= TILE_COLS, "backward TMEM map must fit the tile");
+          static_assert(DH == 16, "transposed images are [16 x 16] blocks");
+          const uint32_t idescB = idesc_tf32(128, 16);
+          const uint32_t sbo1_u = (uint32_t)(K1P >> 2) * 8u;                       // W1 image row-group stride, 16 B units
+          const uint32_t hit = (512u >> 4) | (1u << 14);                            // [16 x 16] blocks: SBO = 4 core matrices
+          const uint32_t w1t_lo = ((smem_u32(w1tbuf) & 0x3FFFFu) >> 4) | lbo;
+          const int NCB = H / 16;
+          auto gemmA = [&](int g, int hc) {
+            const uint32_t tb = tbase + (uint32_t)(g * TILE_COLS);
+            const int c = hc >> 1, hp = hc & 1;
+#pragma unroll
+            for (int net = 0; net < 2; ++net) {
+              const uint32_t grp = (uint32_t)(net * 4 + 2 * hp) * sbo1_u;
+              const uint32_t bh = w1_lo + (uint32_t)(2 * c) * chunk1 + grp, bl = bh + chunk1;
+              const uint32_t dst = tb + D1B + 16 * net;
+#pragma unroll
+              for (int j = 0; j < K1PMAX / 8; ++j)
+                if (j < nk1) mma_tf32_ts(dst, tb + U_LO + 8 * j, desc(bh + 16u * j, hi1), idescB, j ? 1u : 0u);
+#pragma unroll
+              for (int j = 0; j < K1PMAX / 8; ++j)
+                if (j < nk1) mma_tf32_ts(dst, tb + U_HI + 8 * j, desc(bl + 16u * j, hi1), idescB, 1u);
+#pragma unroll
+              for (int j = 0; j < K1PMAX / 8; ++j)
+                if (j < nk1) mma_tf32_ts(dst, tb + U_HI + 8 * j, desc(bh + 16u * j, hi1), idescB, 1u);
+            }
+#pragma unroll
+            for (int net = 0; net < 2; ++net) {
+              const uint32_t bh = w2_lo + (uint32_t)((hc * 2 + net) * 2) * 64u, bl = bh + 64u;
+              const uint32_t dst = tb + DHB + 16 * net;
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                mma_tf32_ts(dst, tb + E2L + 16 * net + 8 * j, desc(bh + 16u * j, hit), idescB, j ? 1u : 0u);
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                mma_tf32_ts(dst, tb + E2H + 16 * net + 8 * j, desc(bl + 16u * j, hit), idescB, 1u);
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                mma_tf32_ts(dst, tb + E2H + 16 * net + 8 * j, desc(bh + 16u * j, hit), idescB, 1u);
+            }
+          };
+          auto gemmB = [&](int g, int hc) {
+            const uint32_t tb = tbase + (uint32_t)(g * TILE_COLS);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {                                       // (net, K half) of this half-chunk
+              const uint32_t bh = w1t_lo + (uint32_t)((hc * 2 + (ks >> 1)) * 2) * 64u + 16u * (ks & 1), bl = bh + 64u;
+              const uint32_t acol = 16 * (ks >> 1) + 8 * (ks & 1);
+              mma_tf32_ts(tb + DUC, tb + D1B + acol, desc(bh, hit), idescB, (hc | ks) ? 1u : 0u);   // delta1_lo * W1_hi
+              mma_tf32_ts(tb + DUC, tb + DHB + acol, desc(bl, hit), idescB, 1u);                    // delta1_hi * W1_lo
+              mma_tf32_ts(tb + DUM, tb + DHB + acol, desc(bh, hit), idescB, (hc | ks) ? 1u : 0u);   // main
+            }
+          };
+          for (int li = 0; li < nL; ++li) {
+            mbar_wait(&bars[B_W1F], ph_w1); ph_w1 ^= 1;
+            mbar_wait(&bars[B_W2F], ph_w2); ph_w2 ^= 1;
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(&bars[B_UF0 + g], ph_u[g]); ph_u[g] ^= 1;
+              fence_after_sync();
+              if (leader) {
+                gemmA(g, 0);
+                if (NCB == 1 && g == 1) mma_commit(&bars[B_W2E]);
+                mma_commit(&bars[B_D1F0 + g]);
+              }
+              __syncwarp();
+            }
+            for (int hc = 0; hc < NCB; ++hc)
+              for (int g = 0; g < 2; ++g) {
+                mbar_wait(&bars[B_AF0 + g], ph_a[g]); ph_a[g] ^= 1;
+                fence_after_sync();
+                if (leader) {
+                  gemmB(g, hc);
+                  if (hc + 1 < NCB) {
+                    gemmA(g, hc + 1);
+                    if (hc + 2 == NCB && g == 1) mma_commit(&bars[B_W2E]);   // last dh of the layer issued
+                    mma_commit(&bars[B_D1F0 + g]);
+                  } else {
+                    if (g == 1) mma_commit(&bars[B_W1E]);                    // last du of the layer issued
+                    mma_commit(&bars[B_D2F0 + g]);
+                  }
+                }
+                __syncwarp();
+              }
+          }
+        }
+      }
+    }   // pairs
   } else {
     // ------------------------------------------------------------------ epilogue: one thread per row
     const int g = (warp - 2) >> 2;                      // tile of the pair
@@ -441,6 +555,128 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
           if (lane == 0) atomicAdd(a.loss_sum, lp);
         }
       }
+
+      // ================================================================ backward sweep (fit step)
+      if constexpr (MODE == 2 && !NETSEQ) {
+        if (a.do_bwd) {
+          constexpr int D1B = 2 * K1PMAX, DHB = D1B + 32, E2H = DHB + 32, E2L = E2H + 32, DUM = E2L + 32, DUC = DUM + 16;
+          const int NCB = H / 16;
+          const int K1P8 = (DH + Cd + 7) & ~7;
+          const long long rloc = pair * 256 + g * 128 + quarter * 32 + lane;       // row inside the padded batch
+          // gradient of scale*sum_rows logp w.r.t. the current activations: g_z = -scale*z, g_logdet = scale
+          const float gld = valid ? a.scale : 0.0f;
+          float ga[DH], gb[DH];
+#pragma unroll
+          for (int e = 0; e < DH; ++e) { ga[e] = -gld * xa[e]; gb[e] = -gld * xb[e]; }
+
+          auto layer_bwd = [&](float (&xT)[DH], float (&xK)[DH], float (&gT)[DH], float (&gK)[DH], int i) {
+            float* rec = a.records + ((size_t)i * a.Npad + rloc) * a.rec;
+            // ---- x_T and s of this layer from the forward stash; delta2 and the new g_T
+            uint32_t e2h[2 * DH], e2l[2 * DH];
+            {
+              const float4* sp = reinterpret_cast<const float4*>(a.stash + ((size_t)row * a.L_total + i) * (2 * DH));
+#pragma unroll
+              for (int m = 0; m < DH / 4; ++m) {
+                const float4 xv = valid ? sp[m] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 sv = valid ? sp[DH / 4 + m] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float xs4[4] = {xv.x, xv.y, xv.z, xv.w}, ss4[4] = {sv.x, sv.y, sv.z, sv.w};
+                float d2t[4], d2s[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int e = 4 * m + q;
+                  const float es = expf(ss4[q]);
+                  xT[e] = xs4[q];                                   // input of this layer (T half)
+                  d2t[q] = gT[e];                                   // dL/dt
+                  d2s[q] = fmaf(gT[e] * xs4[q], es, gld);           // dL/ds = g_y*x*exp(s) + g_logdet
+                  gT[e] *= es;                                      // dL/dx_T
+                  split_tf32(d2t[q], e2h[e], e2l[e]);
+                  split_tf32(d2s[q], e2h[DH + e], e2l[DH + e]);
+                }
+                reinterpret_cast<float4*>(rec + 4 * H + K1P8)[m] = make_float4(d2t[0], d2t[1], d2t[2], d2t[3]);
+                reinterpret_cast<float4*>(rec + 4 * H + K1P8 + DH)[m] = make_float4(d2s[0], d2s[1], d2s[2], d2s[3]);
+              }
+            }
+#pragma unroll
+            for (int e0 = 0; e0 < 2 * DH; e0 += 8) {
+              uint32_t th[8], tl[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { th[j] = e2h[e0 + j]; tl[j] = e2l[e0 + j]; }
+              tmem_st_x8(trow + E2H + e0, th);
+              tmem_st_x8(trow + E2L + e0, tl);
+            }
+            // ---- u = [x_K, c, 1] -> TMEM (conditioning half only, the static part is still in place) and record
+#pragma unroll
+            for (int e0 = 0; e0 < DH; e0 += 8) {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) split_tf32(xK[e0 + j], hi[j], lo[j]);
+              tmem_st_x8(trow + U_HI + e0, hi);
+              tmem_st_x8(trow + U_LO + e0, lo);
+            }
+#pragma unroll
+            for (int m = 0; m < DH / 4; ++m)
+              reinterpret_cast<float4*>(rec + 4 * H)[m] = make_float4(xK[4 * m], xK[4 * m + 1], xK[4 * m + 2], xK[4 * m + 3]);
+#pragma unroll
+            for (int m = 0; m < CDMAX / 4; ++m)
+              if (DH + 4 * m < K1P8)
+                reinterpret_cast<float4*>(rec + 4 * H + DH)[m] = make_float4(cc[4 * m], cc[4 * m + 1], cc[4 * m + 2], cc[4 * m + 3]);
+            tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive(&bars[B_UF0 + g]);
+            // ---- half-chunks: h = act(D1B), delta1 = dh * act'(h); delta1 hi/lo -> TMEM (A operand of du); h, delta1 -> record
+            for (int hc = 0; hc < NCB; ++hc) {
+              mbar_wait(&bars[B_D1F0 + g], ph_d1); ph_d1 ^= 1;
+              fence_after_sync();
+              uint32_t pa[32], dh[32];
+              tmem_ld_x32(trow + D1B, pa);
+              tmem_ld_x32(trow + DHB, dh);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float h = act_mma<ACT>(__uint_as_float(pa[j]));
+                const float dp = ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f);
+                const float d1 = __uint_as_float(dh[j]) * dp;
+                pa[j] = __float_as_uint(h);
+                dh[j] = __float_as_uint(d1);
+              }
+              // record: delta1 at [net][unit], h at 2H + [net][unit]; this half-chunk covers units 16hc.. of both nets
+#pragma unroll
+              for (int net = 0; net < 2; ++net)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                  const int j = 16 * net + 4 * m;
+                  reinterpret_cast<float4*>(rec + net * H + 16 * hc)[m] =
+                      make_float4(__uint_as_float(dh[j]), __uint_as_float(dh[j + 1]), __uint_as_float(dh[j + 2]), __uint_as_float(dh[j + 3]));
+                  reinterpret_cast<float4*>(rec + 2 * H + net * H + 16 * hc)[m] =
+                      make_float4(__uint_as_float(pa[j]), __uint_as_float(pa[j + 1]), __uint_as_float(pa[j + 2]), __uint_as_float(pa[j + 3]));
+                }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(dh[j]), dh[j], pa[j]);     // hi -> dh, lo -> pa
+              tmem_st_x32(trow + DHB, dh);
+              tmem_st_x32(trow + D1B, pa);
+              tmem_wait_st();
+              fence_before_sync();
+              mbar_arrive(&bars[B_AF0 + g]);
+            }
+            // ---- du -> g_x_K
+            mbar_wait(&bars[B_D2F0 + g], ph_d2); ph_d2 ^= 1;
+            fence_after_sync();
+            {
+              uint32_t um[16], uc[16];
+              tmem_ld_x16(trow + DUM, um);
+              tmem_ld_x16(trow + DUC, uc);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < DH; ++e) gK[e] += __uint_as_float(um[e]) + __uint_as_float(uc[e]);
+            }
+          };
+          for (int li = 0; li < nL; ++li) {
+            const int i = a.l1 - 1 - li;
+            if ((i & 1) == 0) layer_bwd(xa, xb, ga, gb, i);
+            else layer_bwd(xb, xa, gb, ga, i);
+          }
+        }
+      }
     }
   }
   fence_before_sync();
@@ -470,8 +706,8 @@ cudaError_t launch_mma_shape(int act, int mode, const RnvpMmaArgs& a, int grid, 
 
 }  // namespace
 
-size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats) {
-  return (size_t)(w1_floats + w2_floats) * 4 + 8 * B_COUNT + 64;
+size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats, int w1t_floats) {
+  return (size_t)(w1_floats + w2_floats + w1t_floats) * 4 + 8 * B_COUNT + 64;
 }
 
 cudaError_t rnvp_launch_mma(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st) {

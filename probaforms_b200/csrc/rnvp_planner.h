@@ -54,6 +54,7 @@ struct FlowGeom {
   int mDH = 0, mCDMAX = 0, mCU = 0, mK1P = 0, mNTP = 0;
   bool m_netseq = false;
   int m_w1_floats = 0, m_w2_floats = 0, m_b2_floats = 0, m_layer_floats = 0;
+  int m_wt_floats = 0;   // transposed images for the backward sweep (W2T then W1T, m_wt_floats each), 0 if not built
   int64_t mma_off = 0, mma_floats = 0;
 };
 
@@ -125,7 +126,10 @@ inline void build_layout(FlowGeom* d) {
       d->mDH = DH; d->mCDMAX = CDMAX; d->mCU = CU; d->mK1P = K1P; d->mNTP = NTP; d->m_netseq = netseq;
       d->m_b2_floats = 32 * NTP;                               // 2 nets x [hi | lo] x [NTP x 8]
       d->m_w1_floats = (int)w1; d->m_w2_floats = (int)w2 + d->m_b2_floats;  // b2 images ride with the W2 copy
-      d->m_layer_floats = d->m_w1_floats + d->m_w2_floats;
+      // backward sweep (concurrent-net kernels only): K-major images of the transposed operands, per half-chunk of 16
+      // units and net a [16 x 16] block [hi | lo]: W2T (units x transformed features) and W1T (x_K columns x units)
+      d->m_wt_floats = (!netseq && H % 16 == 0 && H <= 128) ? 4 * H * 16 : 0;
+      d->m_layer_floats = d->m_w1_floats + d->m_w2_floats + 2 * d->m_wt_floats;
       d->mma_off = (d->packed + 31) & ~(int64_t)31;            // 128-byte aligned for the bulk copies
       d->mma_floats = (int64_t)d->L * d->m_layer_floats;
       d->packed = d->mma_off + d->mma_floats;
@@ -187,6 +191,22 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
           const int ft = lg.par == 0 ? 2 * r : 2 * r + 1;
           m2f[base3 + (net * 2 + part) * (NTP * 8) + mma_tiled_off(r, (DH + Cd) & 7, 8)] = (int)(4 * (g1.flat_b[net] + ft) + part);
         }
+    if (d->m_wt_floats) {
+      const int64_t base4 = base2 + d->m_w2_floats, base5 = base4 + d->m_wt_floats;
+      for (int hc = 0; hc < H / 16; ++hc)
+        for (int net = 0; net < 2; ++net)
+          for (int part = 0; part < 2; ++part) {
+            const int64_t off = (((int64_t)hc * 2 + net) * 2 + part) * 256;
+            for (int un = 0; un < 16; ++un)
+              for (int e = 0; e < DH; ++e) {
+                const int unit = hc * 16 + un;
+                const int ft = lg.par == 0 ? 2 * e : 2 * e + 1;            // transformed feature e
+                const int xk = lg.par == 0 ? 2 * e + 1 : 2 * e;            // conditioning feature e
+                m2f[base4 + off + mma_tiled_off(un, e, 16)] = (int)(4 * (g1.flat_w[net] + (int64_t)ft * H + unit) + part);
+                m2f[base5 + off + mma_tiled_off(e, un, 16)] = (int)(4 * (g0.flat_w[net] + (int64_t)unit * (D + Cd) + xk) + part);
+              }
+          }
+    }
   }
 }
 

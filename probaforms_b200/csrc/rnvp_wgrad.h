@@ -1,0 +1,19 @@
+// Arguments of the weight-gradient sweep kernel (rnvp_wgrad.cu).
+#pragma once
+#include <stdint.h>
+
+struct RnvpWgradLayer {            // where one layer's gradients live in the packed accumulator (tile layout)
+  int w1_off[2], b1_off[2];        // first Linear of nn_t / nn_s: rows = hidden units, row stride Ks1
+  int w2_off[2], b2_off[2];        // last Linear: rows = transformed features, row stride Ks2
+  int Ks1, Ks2;
+};
+
+struct RnvpWgradArgs {
+  const float* gR;                 // records [L][Npad][rec]: delta1 (2H) | h (2H) | u (K1P) | delta2 (2*TP) | pad
+  int rec;                         // record stride in floats, == 8 (mod 32)
+  float* gpacked;
+  const RnvpWgradLayer* layers;    // device array, L entries
+  long long Npad;                  // rows, multiple of 32; padding rows hold zeros in delta1 / delta2
+  int n_slices;                    // row slices per layer; grid = L * n_slices
+  int H;
+};
