@@ -111,9 +111,11 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
 
 /* Weight-gradient sweep from stored activations (last part of a fit step on the tcgen05 path): for every layer
  * dW1 += delta1^T u, db1 += sum delta1, dW2 += delta2^T h, db2 += sum delta2 (sums over rows), accumulated into
- * d_gpacked.  d_records is [L][Npad][rec] with rec = rnvp_wgrad_record_floats(d) and one record per (layer, row):
- * delta1 [2][H] (nn_t | nn_s) | h [2][H] | u = [x_K, c, 0..] (ceil8(D/2+Cd)) | delta2 [2][D/2] | padding.
- * Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.  tcgen05-eligible flows, H <= 128. */
+ * d_gpacked.  One record of rec = rnvp_wgrad_record_floats(d) floats per (layer, row):
+ * delta1 [2][H] (nn_t | nn_s) | h [2][H] | u = [x_K, c, 0..] (ceil8(D/2+Cd)) | delta2 [2][D/2],
+ * stored in blocks of 32 rows as d_records[L][Npad/32][rec/4][32][4]: float4 column group q of row r of a block sits
+ * in slot (r ^ 4*(q & 1)).  Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.
+ * tcgen05-eligible flows with D = 32, H <= 128. */
 int rnvp_wgrad_record_floats(const rnvp_desc* d);
 int rnvp_wgrad_sweep(const rnvp_desc* d, int64_t Npad, const float* d_records, float* d_gpacked, void* stream);
 

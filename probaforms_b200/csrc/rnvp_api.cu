@@ -250,8 +250,7 @@ bool use_mma_bwd(const rnvp_desc* d) { return use_mma(d) && d->m_wt_floats > 0; 
 // record stride of the activation records exchanged between the backward sweep and the weight-gradient sweep
 int wgrad_rec_floats(const rnvp_desc* d) {
   const int K1P = (d->mDH + d->Cd + 7) & ~7;
-  const int n = 4 * d->hidden[0] + K1P + 2 * d->mDH;
-  return ((n + 31) & ~31) + 8;
+  return 4 * d->hidden[0] + K1P + 2 * d->mDH;               // multiple of 8: an even number of float4 column groups
 }
 
 int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
@@ -566,7 +565,7 @@ int rnvp_wgrad_sweep(const rnvp_desc* dc, int64_t Npad, const float* d_records, 
   RnvpWgradArgs a;
   a.gR = d_records; a.rec = wgrad_rec_floats(d); a.gpacked = d_gpacked; a.layers = d->d_wg;
   a.Npad = Npad; a.H = d->hidden[0];
-  a.n_slices = (int)std::max<long long>(1, std::min<long long>(Npad / 32, (d->num_sms + d->L - 1) / d->L));
+  a.n_slices = (int)std::max<long long>(1, std::min<long long>(Npad / 32, d->num_sms / d->L));   // one wave of CTAs
   cudaError_t e = rnvp_launch_wgrad(K1P / 8, TP / 8, a, d->L * a.n_slices, rnvp_wgrad_smem_bytes(a.rec, K1P + 2 * TP), (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "rnvp_wgrad_kernel");
 }

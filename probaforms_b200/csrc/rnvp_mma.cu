@@ -570,7 +570,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
           for (int e = 0; e < DH; ++e) { ga[e] = -gld * xa[e]; gb[e] = -gld * xb[e]; }
 
           auto layer_bwd = [&](float (&xT)[DH], float (&xK)[DH], float (&gT)[DH], float (&gK)[DH], int i) {
-            float* rec = a.records + ((size_t)i * a.Npad + rloc) * a.rec;
+            // records: [layer][block of 32 rows][column group of 4][32 slots][4 floats], slot = (row % 32) ^ 4*(group & 1):
+            // a warp-level float4 store covers 512 contiguous bytes, and the weight-gradient sweep's mma fragment loads
+            // of a block are bank-conflict free (rnvp_wgrad.cu)
+            float* recb = a.records + (((size_t)i * (size_t)(a.Npad >> 5) + (size_t)(rloc >> 5)) * (size_t)(a.rec >> 2)) * 128;
+            auto rec_st = [&](int col, float4 v) {
+              const int cg = col >> 2;
+              *reinterpret_cast<float4*>(recb + cg * 128 + ((lane ^ ((cg & 1) << 2)) << 2)) = v;
+            };
             // ---- x_T and s of this layer from the forward stash; delta2 and the new g_T
             uint32_t e2h[2 * DH], e2l[2 * DH];
             {
@@ -592,8 +599,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                   split_tf32(d2t[q], e2h[e], e2l[e]);
                   split_tf32(d2s[q], e2h[DH + e], e2l[DH + e]);
                 }
-                reinterpret_cast<float4*>(rec + 4 * H + K1P8)[m] = make_float4(d2t[0], d2t[1], d2t[2], d2t[3]);
-                reinterpret_cast<float4*>(rec + 4 * H + K1P8 + DH)[m] = make_float4(d2s[0], d2s[1], d2s[2], d2s[3]);
+                rec_st(4 * H + K1P8 + 4 * m, make_float4(d2t[0], d2t[1], d2t[2], d2t[3]));
+                rec_st(4 * H + K1P8 + DH + 4 * m, make_float4(d2s[0], d2s[1], d2s[2], d2s[3]));
               }
             }
 #pragma unroll
@@ -615,11 +622,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             }
 #pragma unroll
             for (int m = 0; m < DH / 4; ++m)
-              reinterpret_cast<float4*>(rec + 4 * H)[m] = make_float4(xK[4 * m], xK[4 * m + 1], xK[4 * m + 2], xK[4 * m + 3]);
+              rec_st(4 * H + 4 * m, make_float4(xK[4 * m], xK[4 * m + 1], xK[4 * m + 2], xK[4 * m + 3]));
 #pragma unroll
             for (int m = 0; m < CDMAX / 4; ++m)
               if (DH + 4 * m < K1P8)
-                reinterpret_cast<float4*>(rec + 4 * H + DH)[m] = make_float4(cc[4 * m], cc[4 * m + 1], cc[4 * m + 2], cc[4 * m + 3]);
+                rec_st(4 * H + DH + 4 * m, make_float4(cc[4 * m], cc[4 * m + 1], cc[4 * m + 2], cc[4 * m + 3]));
             tmem_wait_st();
             fence_before_sync();
             mbar_arrive(&bars[B_UF0 + g]);
@@ -645,10 +652,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                   const int j = 16 * net + 4 * m;
-                  reinterpret_cast<float4*>(rec + net * H + 16 * hc)[m] =
-                      make_float4(__uint_as_float(dh[j]), __uint_as_float(dh[j + 1]), __uint_as_float(dh[j + 2]), __uint_as_float(dh[j + 3]));
-                  reinterpret_cast<float4*>(rec + 2 * H + net * H + 16 * hc)[m] =
-                      make_float4(__uint_as_float(pa[j]), __uint_as_float(pa[j + 1]), __uint_as_float(pa[j + 2]), __uint_as_float(pa[j + 3]));
+                  rec_st(net * H + 16 * hc + 4 * m,
+                         make_float4(__uint_as_float(dh[j]), __uint_as_float(dh[j + 1]), __uint_as_float(dh[j + 2]), __uint_as_float(dh[j + 3])));
+                  rec_st(2 * H + net * H + 16 * hc + 4 * m,
+                         make_float4(__uint_as_float(pa[j]), __uint_as_float(pa[j + 1]), __uint_as_float(pa[j + 2]), __uint_as_float(pa[j + 3])));
                 }
 #pragma unroll
               for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(dh[j]), dh[j], pa[j]);     // hi -> dh, lo -> pa

@@ -9,8 +9,8 @@ struct RnvpWgradLayer {            // where one layer's gradients live in the pa
 };
 
 struct RnvpWgradArgs {
-  const float* gR;                 // records [L][Npad][rec]: delta1 (2H) | h (2H) | u (K1P) | delta2 (2*TP) | pad
-  int rec;                         // record stride in floats, == 8 (mod 32)
+  const float* gR;                 // records [L][Npad/32][rec/4][32][4]: delta1 (2H) | h (2H) | u (K1P) | delta2 (2*TP)
+  int rec;                         // floats per record (multiple of 8)
   float* gpacked;
   const RnvpWgradLayer* layers;    // device array, L entries
   long long Npad;                  // rows, multiple of 32; padding rows hold zeros in delta1 / delta2

@@ -23,6 +23,11 @@ R[:, :, 2 * H:4 * H] = h.reshape(L, N, 2 * H)
 R[:, :, 4 * H:4 * H + K1P] = u
 R[:, :, 4 * H + K1P:4 * H + K1P + D] = d2.reshape(L, N, D)
 print('record floats', rec)
+# blocked layout of the C ABI: [L][N/32][rec/4][32 slots][4], slot = row ^ 4*(group & 1)
+Rb = R.view(L, N // 32, 32, rec // 4, 4).permute(0, 1, 3, 2, 4).contiguous()
+perm = torch.arange(32, device=dev) ^ 4
+Rb[:, :, 1::2] = Rb[:, :, 1::2][:, :, :, perm]
+R = Rb
 def run():
     _lib.check(eng.lib.rnvp_wgrad_sweep(eng._desc, N, P(R), P(eng.gpacked), None), 'wgrad')
 eng.zero_grads(); run(); torch.cuda.synchronize()
