@@ -111,18 +111,24 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
 
 /* Weight-gradient sweep from stored activations (last part of a fit step on the tcgen05 path): for every layer
  * dW1 += delta1^T u, db1 += sum delta1, dW2 += delta2^T h, db2 += sum delta2 (sums over rows), accumulated into
- * d_gpacked.  One record of rec = rnvp_wgrad_record_floats(d) floats per (layer, row):
- * delta1 [2][H] (nn_t | nn_s) | h [2][H] | u = [x_K, c, 0..] (ceil8(D/2+Cd)) | delta2 [2][D/2],
+ * d_gpacked, with delta1 = (delta2 W2) * act'(h) recomputed from d_packed.  One record of
+ * rec = rnvp_wgrad_record_floats(d) floats per (layer, row):
+ * h [2][H] (nn_t | nn_s) | u = [x_K, c, 0..] (ceil8(D/2+Cd)) | delta2 [2][D/2],
  * stored in blocks of 32 rows as d_records[L][Npad/32][rec/4][32][4]: float4 column group q of row r of a block sits
- * in slot (r ^ 4*(q & 1)).  Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.
+ * in slot (r ^ (q & 1)).  Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.
  * tcgen05-eligible flows with D = 32, H <= 128. */
 int rnvp_wgrad_record_floats(const rnvp_desc* d);
-int rnvp_wgrad_sweep(const rnvp_desc* d, int64_t Npad, const float* d_records, float* d_gpacked, void* stream);
+int rnvp_wgrad_sweep(const rnvp_desc* d, const float* d_packed, int64_t Npad, const float* d_records, float* d_gpacked,
+                     void* stream);
 
 /* Kernel-family selection for rnvp_forward / rnvp_inverse: 0 = auto (tcgen05 TF32x3 kernels where the shape is
  * eligible -- one hidden layer, D/2 in {16,32} --, else the small-flow or FP32 tile kernels), 1 = FP32-FMA kernels
  * only, 2 = same as auto.  rnvp_plan_info reports the family chosen (0 tile, 1 small-flow, 2 tcgen05). */
 int rnvp_set_path(rnvp_desc* d, int path);
+
+/* Development aid: when d_buf (device, 3*2048*2 int64) is non-null, CTA 0 of the tcgen05 fit kernel logs (tag, clock64)
+ * pairs of its backward sweep (tile-0 epilogue, tile-1 epilogue, MMA issuer); tools/trace_mma.py prints the timeline. */
+int rnvp_debug_set_trace(void* d_buf);
 
 /* Tensor-core primitive self-test (tcgen05.mma kind::tf32, A in TMEM, B in shared memory):
  * D[128,N] = A[128,K] * B[N,K]^T on device buffers; passes = 1 (plain TF32) or 3 (split, fp32-grade). */

@@ -43,8 +43,9 @@ SIGNATURES = {
                                  C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.c_int64, C.c_int, c_f32_p, c_f32_p, C.c_float, c_stream]),
     "rnvp_wgrad_record_floats": (C.c_int, [c_desc_p]),
-    "rnvp_wgrad_sweep": (C.c_int, [c_desc_p, C.c_int64, c_f32_p, c_f32_p, c_stream]),
+    "rnvp_wgrad_sweep": (C.c_int, [c_desc_p, c_f32_p, C.c_int64, c_f32_p, c_f32_p, c_stream]),
     "rnvp_set_path": (C.c_int, [c_desc_p, C.c_int]),
+    "rnvp_debug_set_trace": (C.c_int, [C.c_void_p]),
     "rnvp_mma_selftest": (C.c_int, [c_f32_p, c_f32_p, c_f32_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "rnvp_last_error": (C.c_char_p, []),
     "rnvp_version": (C.c_int, []),

@@ -244,13 +244,14 @@ int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const
   return 0;
 }
 
+long long* g_mma_trace = nullptr;   // development aid, see rnvp_debug_set_trace
 bool use_mma(const rnvp_desc* d) { return d->mma_ok && d->path != 1; }
 // fit step entirely on the tensor-core path (tcgen05 forward + backward sweeps, mma.sync weight-gradient sweep)
 bool use_mma_bwd(const rnvp_desc* d) { return use_mma(d) && d->m_wt_floats > 0; }
 // record stride of the activation records exchanged between the backward sweep and the weight-gradient sweep
 int wgrad_rec_floats(const rnvp_desc* d) {
   const int K1P = (d->mDH + d->Cd + 7) & ~7;
-  return 4 * d->hidden[0] + K1P + 2 * d->mDH;               // multiple of 8: an even number of float4 column groups
+  return 2 * d->hidden[0] + K1P + 2 * d->mDH;               // multiple of 8: an even number of float4 column groups
 }
 
 int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
@@ -267,6 +268,7 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.stash = stash; a.loss_sum = loss_sum; a.L_total = d->L;
   a.do_bwd = records != nullptr; a.scale = scale; a.records = records; a.rec = 0; a.Npad = 0;
   a.wt_floats = records ? d->m_wt_floats : 0;
+  a.trace = g_mma_trace;
   const long long pairs = (N + 255) / 256;
   if (pairs > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
   a.n_pairs = (int)pairs;
@@ -504,7 +506,7 @@ int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, 
     int rc = run_mma(d, 2, 0, d->L, d_packed, d_X, d_C, (const long long*)d_idx, N, nullptr, nullptr, d_logp,
                      (cudaStream_t)stream, stash, d_logp_sum, records, scale);
     if (rc) return rc;
-    return rnvp_wgrad_sweep(d, npad, records, d_gpacked, stream);
+    return rnvp_wgrad_sweep(d, d_packed, npad, records, d_gpacked, stream);
   }
   if (use_mma(d) && N > 0) {
     // forward sweep on the tensor cores (z, per-layer x_T and s to the workspace), backward sweep on the FP32 tile kernel
@@ -554,21 +556,25 @@ int rnvp_wgrad_record_floats(const rnvp_desc* d) {
   return wgrad_rec_floats(d);
 }
 
-int rnvp_wgrad_sweep(const rnvp_desc* dc, int64_t Npad, const float* d_records, float* d_gpacked, void* stream) {
+int rnvp_wgrad_sweep(const rnvp_desc* dc, const float* d_packed, int64_t Npad, const float* d_records, float* d_gpacked,
+                     void* stream) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
   if (check_desc(d)) return RNVP_EINVAL;
   if (!d->mma_ok || 2 * d->hidden[0] > 256 || d->hidden[0] % 16)
     return fail(RNVP_ESHAPE, "rnvp_wgrad_sweep: needs a tcgen05-eligible flow with hidden width <= 128 (multiple of 16)");
-  if (!d_records || !d_gpacked) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: null buffer");
+  if (!d_records || !d_gpacked || !d_packed) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: null buffer");
   if (Npad <= 0 || Npad % 32) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: Npad must be a positive multiple of 32");
   const int K1P = (d->mDH + d->Cd + 7) & ~7, TP = d->mDH;
   RnvpWgradArgs a;
   a.gR = d_records; a.rec = wgrad_rec_floats(d); a.gpacked = d_gpacked; a.layers = d->d_wg;
+  a.packed = d_packed; a.act = d->act;
   a.Npad = Npad; a.H = d->hidden[0];
   a.n_slices = (int)std::max<long long>(1, std::min<long long>(Npad / 32, d->num_sms / d->L));   // one wave of CTAs
   cudaError_t e = rnvp_launch_wgrad(K1P / 8, TP / 8, a, d->L * a.n_slices, rnvp_wgrad_smem_bytes(a.rec, K1P + 2 * TP), (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "rnvp_wgrad_kernel");
 }
+
+int rnvp_debug_set_trace(void* d_buf) { g_mma_trace = (long long*)d_buf; return 0; }
 
 int rnvp_set_path(rnvp_desc* d, int path) {
   if (check_desc(d)) return RNVP_EINVAL;

@@ -126,6 +126,15 @@ __device__ __forceinline__ float act_mma(float v) {
   return fmaxf(v, 0.0f);
 }
 
+// trace slot `who` (0 / 1: epilogue group of tile 0 / 1, 2: MMA issuer) of CTA 0: (tag, clock64), 2048 events per slot
+__device__ __forceinline__ void trace_ev(const RnvpMmaArgs& a, int who, int& n, int tag) {
+  if (a.trace && blockIdx.x == 0 && n < 2048) {
+    a.trace[(who * 2048 + n) * 2] = tag;
+    a.trace[(who * 2048 + n) * 2 + 1] = clock64();
+    ++n;
+  }
+}
+
 enum { B_W1F = 0, B_W1E, B_W2F, B_W2E, B_UF0, B_UF1, B_D1F0, B_D1F1, B_AF0, B_AF1, B_D2F0, B_D2F1, B_COUNT };
 
 template <int DH, int CDMAX, int CU, bool NETSEQ, int ACT, int MODE>
@@ -356,13 +365,16 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
               mma_tf32_ts(tb + DUM, tb + DHB + acol, desc(bh, hit), idescB, (hc | ks) ? 1u : 0u);   // main
             }
           };
+          int ntr = 0;
           for (int li = 0; li < nL; ++li) {
             mbar_wait(&bars[B_W1F], ph_w1); ph_w1 ^= 1;
             mbar_wait(&bars[B_W2F], ph_w2); ph_w2 ^= 1;
+            if (leader) trace_ev(a, 2, ntr, 200 + li);
             for (int g = 0; g < 2; ++g) {
               mbar_wait(&bars[B_UF0 + g], ph_u[g]); ph_u[g] ^= 1;
               fence_after_sync();
               if (leader) {
+                trace_ev(a, 2, ntr, 300 + g);
                 gemmA(g, 0);
                 if (NCB == 1 && g == 1) mma_commit(&bars[B_W2E]);
                 mma_commit(&bars[B_D1F0 + g]);
@@ -374,6 +386,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                 mbar_wait(&bars[B_AF0 + g], ph_a[g]); ph_a[g] ^= 1;
                 fence_after_sync();
                 if (leader) {
+                  trace_ev(a, 2, ntr, 400 + 2 * hc + g);
                   gemmB(g, hc);
                   if (hc + 1 < NCB) {
                     gemmA(g, hc + 1);
@@ -383,6 +396,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                     if (g == 1) mma_commit(&bars[B_W1E]);                    // last du of the layer issued
                     mma_commit(&bars[B_D2F0 + g]);
                   }
+                  trace_ev(a, 2, ntr, 500 + 2 * hc + g);
                 }
                 __syncwarp();
               }
@@ -569,14 +583,17 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 #pragma unroll
           for (int e = 0; e < DH; ++e) { ga[e] = -gld * xa[e]; gb[e] = -gld * xb[e]; }
 
+          int ntr = 0;
+          const bool tracer = quarter == 0 && lane == 0;
           auto layer_bwd = [&](float (&xT)[DH], float (&xK)[DH], float (&gT)[DH], float (&gK)[DH], int i) {
-            // records: [layer][block of 32 rows][column group of 4][32 slots][4 floats], slot = (row % 32) ^ 4*(group & 1):
+            if (tracer) trace_ev(a, g, ntr, 100 + i);
+            // records: [layer][block of 32 rows][column group of 4][32 slots][4 floats], slot = (row % 32) ^ (group & 1):
             // a warp-level float4 store covers 512 contiguous bytes, and the weight-gradient sweep's mma fragment loads
             // of a block are bank-conflict free (rnvp_wgrad.cu)
             float* recb = a.records + (((size_t)i * (size_t)(a.Npad >> 5) + (size_t)(rloc >> 5)) * (size_t)(a.rec >> 2)) * 128;
             auto rec_st = [&](int col, float4 v) {
               const int cg = col >> 2;
-              *reinterpret_cast<float4*>(recb + cg * 128 + ((lane ^ ((cg & 1) << 2)) << 2)) = v;
+              *reinterpret_cast<float4*>(recb + cg * 128 + ((lane ^ (cg & 1)) << 2)) = v;
             };
             // ---- x_T and s of this layer from the forward stash; delta2 and the new g_T
             uint32_t e2h[2 * DH], e2l[2 * DH];
@@ -599,8 +616,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                   split_tf32(d2t[q], e2h[e], e2l[e]);
                   split_tf32(d2s[q], e2h[DH + e], e2l[DH + e]);
                 }
-                rec_st(4 * H + K1P8 + 4 * m, make_float4(d2t[0], d2t[1], d2t[2], d2t[3]));
-                rec_st(4 * H + K1P8 + DH + 4 * m, make_float4(d2s[0], d2s[1], d2s[2], d2s[3]));
+                rec_st(2 * H + K1P8 + 4 * m, make_float4(d2t[0], d2t[1], d2t[2], d2t[3]));
+                rec_st(2 * H + K1P8 + DH + 4 * m, make_float4(d2s[0], d2s[1], d2s[2], d2s[3]));
               }
             }
 #pragma unroll
@@ -622,18 +639,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             }
 #pragma unroll
             for (int m = 0; m < DH / 4; ++m)
-              rec_st(4 * H + 4 * m, make_float4(xK[4 * m], xK[4 * m + 1], xK[4 * m + 2], xK[4 * m + 3]));
+              rec_st(2 * H + 4 * m, make_float4(xK[4 * m], xK[4 * m + 1], xK[4 * m + 2], xK[4 * m + 3]));
 #pragma unroll
             for (int m = 0; m < CDMAX / 4; ++m)
               if (DH + 4 * m < K1P8)
-                rec_st(4 * H + DH + 4 * m, make_float4(cc[4 * m], cc[4 * m + 1], cc[4 * m + 2], cc[4 * m + 3]));
+                rec_st(2 * H + DH + 4 * m, make_float4(cc[4 * m], cc[4 * m + 1], cc[4 * m + 2], cc[4 * m + 3]));
             tmem_wait_st();
             fence_before_sync();
             mbar_arrive(&bars[B_UF0 + g]);
+            if (tracer) trace_ev(a, g, ntr, 2);
             // ---- half-chunks: h = act(D1B), delta1 = dh * act'(h); delta1 hi/lo -> TMEM (A operand of du); h, delta1 -> record
             for (int hc = 0; hc < NCB; ++hc) {
               mbar_wait(&bars[B_D1F0 + g], ph_d1); ph_d1 ^= 1;
               fence_after_sync();
+              if (tracer) trace_ev(a, g, ntr, 10 + hc);
               uint32_t pa[32], dh[32];
               tmem_ld_x32(trow + D1B, pa);
               tmem_ld_x32(trow + DHB, dh);
@@ -646,15 +665,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                 pa[j] = __float_as_uint(h);
                 dh[j] = __float_as_uint(d1);
               }
-              // record: delta1 at [net][unit], h at 2H + [net][unit]; this half-chunk covers units 16hc.. of both nets
+              // record: h at [net][unit] (the weight-gradient sweep recomputes delta1 from delta2 and h); this half-chunk
+              // covers units 16hc.. of both nets
 #pragma unroll
               for (int net = 0; net < 2; ++net)
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                   const int j = 16 * net + 4 * m;
                   rec_st(net * H + 16 * hc + 4 * m,
-                         make_float4(__uint_as_float(dh[j]), __uint_as_float(dh[j + 1]), __uint_as_float(dh[j + 2]), __uint_as_float(dh[j + 3])));
-                  rec_st(2 * H + net * H + 16 * hc + 4 * m,
                          make_float4(__uint_as_float(pa[j]), __uint_as_float(pa[j + 1]), __uint_as_float(pa[j + 2]), __uint_as_float(pa[j + 3])));
                 }
 #pragma unroll
@@ -664,10 +682,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
               tmem_wait_st();
               fence_before_sync();
               mbar_arrive(&bars[B_AF0 + g]);
+              if (tracer) trace_ev(a, g, ntr, 30 + hc);
             }
             // ---- du -> g_x_K
             mbar_wait(&bars[B_D2F0 + g], ph_d2); ph_d2 ^= 1;
             fence_after_sync();
+            if (tracer) trace_ev(a, g, ntr, 60);
             {
               uint32_t um[16], uc[16];
               tmem_ld_x16(trow + DUM, um);

@@ -20,11 +20,12 @@ struct RnvpMmaArgs {
   float* loss_sum;
   int L_total;                 // layers of the flow (stash row = L_total * 2 * DH floats)
   // MODE 2 with do_bwd: the kernel continues with the backward sweep (everything but the weight gradients): per (layer,
-  // row) it leaves a record [delta1 2H | h 2H | u K1P8 | delta2 2*DH | pad] in records[L][Npad][rec] for rnvp_wgrad_kernel
+  // row) it leaves a record [h 2H | u K1P8 | delta2 2*DH] in the blocked records array (rnvp_wgrad.cu) for rnvp_wgrad_kernel
   int do_bwd;
   float scale;                 // d(out)/d(logp_row): g_logdet = scale, g_z = -scale*z
   float* records;
   int rec;
   long long Npad;
+  long long* trace;            // development aid (rnvp_debug_set_trace): CTA 0 logs (tag, clock64) pairs of the backward sweep
   int wt_floats;               // floats of one transposed image (W2T, then W1T) per layer; 0 unless do_bwd
 };

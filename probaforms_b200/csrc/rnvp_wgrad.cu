@@ -5,8 +5,9 @@
 //     dW1[j][k] = sum_r delta1[r][j] * u[r][k]      db1[j] = sum_r delta1[r][j]       (first Linear of nn_t | nn_s)
 //     dW2[i][j] = sum_r delta2[r][i] * h[r][j]      db2[i] = sum_r delta2[r][i]       (last Linear)
 // i.e. tall-skinny GEMMs with K = rows.  The backward sweep leaves one record per (layer, row),
-//     [ delta1 (2H: nn_t | nn_s) | h (2H) | u = [x_K, c, 0..] (K1P) | delta2 (2*TP: t | s) ]   (REC floats)
-// stored in blocks of 32 rows as [layer][block][column group of 4][32 slots][4] (slot = row ^ 4*(group & 1)): the backward
+//     [ h (2H: nn_t | nn_s) | u = [x_K, c, 0..] (K1P) | delta2 (2*TP: t | s) ]   (REC floats)
+// (delta1 = (delta2 W2) * act'(h) is recomputed here: one more small MMA instead of 1 KB of HBM traffic per layer-row),
+// stored in blocks of 32 rows as [layer][block][column group of 4][32 slots][4] (slot = row ^ (group & 1)): the backward
 // sweep's per-row float4 stores coalesce to 512 B per warp, a block is ONE contiguous TMA bulk copy, and every mma
 // fragment load from it is bank-conflict free.  This kernel streams the array (written once, read once) through a
 // 3-stage ring and contracts with warp-level mma.sync.m16n8k8 TF32 in the error-compensated
@@ -38,8 +39,8 @@ __device__ __forceinline__ void mma_1688(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// float offset of (column c, row r) inside a 32-row block: [column group of 4][32 slots][4], slot = r ^ 4*(group & 1)
-__device__ __forceinline__ int blk_off(int c, int r) { return (c >> 2) * 128 + ((r ^ (((c >> 2) & 1) << 2)) << 2) + (c & 3); }
+// float offset of (column c, row r) inside a 32-row block: [column group of 4][32 slots][4], slot = r ^ (group & 1)
+__device__ __forceinline__ int blk_off(int c, int r) { return (c >> 2) * 128 + ((r ^ ((c >> 2) & 1)) << 2) + (c & 3); }
 
 // NT1 = 8-wide column tiles of dW1 (ceil8(|K|+Cd)/8), NT2 = column tiles of dW2 per net (|T|/8)
 template <int NT1, int NT2>
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) rnvp_wgrad_kernel(const __grid_
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int H = a.H, H2 = 2 * H, K1P = NT1 * 8, TP = NT2 * 8;
-  const int REC = a.rec;                                           // floats per record = 4H + K1P + 2*TP
+  const int REC = a.rec;                                           // floats per record = 2H + K1P + 2*TP
   const int stage_floats = WG_ROWS * REC;
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + WG_STAGES * stage_floats);
   uint64_t* empty = full + WG_STAGES;
@@ -103,7 +104,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) rnvp_wgrad_kernel(const __grid_
   const int j0 = 16 * warp;
   const int net = active ? j0 / H : 0;                       // m-tile lies entirely in one net (H % 16 == 0)
   const bool sums_b2 = active && (j0 == net * H);
-  const int cD = j0 + g, cH = H2 + j0 + g, cU = 2 * H2 + g, cE = 2 * H2 + K1P + net * TP + g;
+  // Stage-relative float offsets of this thread's fragment elements (see blk_off): every column it touches is
+  // (multiple of 8) + g, so the slot swizzle bit is par = (g >> 2) & 1 for all of them and rows r0+2t / r0+2t+1 sit in
+  // slots r0 + (2t ^ par) / r0 + ((2t+1) ^ par); r0, the column tile j and the K step are compile-time immediates.
+  const int par = (g >> 2) & 1;
+  const int oa = (g >> 2) * 128 + ((2 * t) ^ par) * 4 + (g & 3), ob = (g >> 2) * 128 + ((2 * t + 1) ^ par) * 4 + (g & 3);
+  const int iH = (j0 >> 2) * 128, iU = (H2 >> 2) * 128, iE = ((H2 + K1P + net * TP) >> 2) * 128;
+  // B operand of the dh product: column (8kk + t) of delta2 (group parity 0) and column (8kk + 4 + t) (parity 1), row r0+g
+  const int iB0 = iE + g * 4 + t, iB1 = iE + 128 + (g ^ 1) * 4 + t;
+  // delta1 is not stored: dh = delta2 W2 is recomputed here (K = TP) and delta1 = dh * act'(h).  A operand of that product:
+  // this warp's 16 columns of W2 (rows = transformed features), TF32 hi / lo, loaded once
+  uint32_t wh[NT2][4], wl[NT2][4];
+  {
+    const RnvpWgradLayer& lw0 = a.layers[layer];
+    const float* w2 = a.packed + lw0.w2_off[net];
+    const int u0 = j0 + g - net * H;
+#pragma unroll
+    for (int kk = 0; kk < NT2; ++kk) {
+      const float v0 = active ? w2[(8 * kk + t) * lw0.Ks2 + u0] : 0.f, v1 = active ? w2[(8 * kk + t) * lw0.Ks2 + u0 + 8] : 0.f;
+      const float v2 = active ? w2[(8 * kk + t + 4) * lw0.Ks2 + u0] : 0.f, v3 = active ? w2[(8 * kk + t + 4) * lw0.Ks2 + u0 + 8] : 0.f;
+      split_frag(v0, wh[kk][0], wl[kk][0]);
+      split_frag(v1, wh[kk][1], wl[kk][1]);
+      split_frag(v2, wh[kk][2], wl[kk][2]);
+      split_frag(v3, wh[kk][3], wl[kk][3]);
+    }
+  }
+  const bool is_tanh = a.act == 1;
 
   for (long long b = 0; b < nblk; ++b) {
     const int st = (int)(b % WG_STAGES);
@@ -114,34 +140,57 @@ __global__ void __launch_bounds__(WG_THREADS, 1) rnvp_wgrad_kernel(const __grid_
 #pragma unroll
       for (int r0 = 0; r0 < WG_ROWS; r0 += 8) {
         if (tid == 0 && r0) produce(b);
-        const int ra = r0 + t, rb = r0 + t + 4;
+        // rows of this thread's K slots: the dh product below leaves delta1 in accumulator layout (unit g / g+8, rows
+        // 2t / 2t+1 of the 8); used as the A fragment of the gradient products that makes K slot t <-> row 2t and K slot
+        // t+4 <-> row 2t+1, and the B fragments (u, delta2) and h are read with the same row permutation
+        float dm[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+          uint32_t bh[NT2][2], bl[NT2][2];
+#pragma unroll
+          for (int kk = 0; kk < NT2; ++kk) {
+            split_frag(S[iB0 + 256 * kk + 4 * r0], bh[kk][0], bl[kk][0]);
+            split_frag(S[iB1 + 256 * kk + 4 * r0], bh[kk][1], bl[kk][1]);
+          }
+#pragma unroll
+          for (int kk = 0; kk < NT2; ++kk) mma_1688(dc, wl[kk], bh[kk][0], bh[kk][1]);
+#pragma unroll
+          for (int kk = 0; kk < NT2; ++kk) mma_1688(dm, wh[kk], bh[kk][0], bh[kk][1]);
+#pragma unroll
+          for (int kk = 0; kk < NT2; ++kk) mma_1688(dc, wh[kk], bl[kk][0], bl[kk][1]);
+        }
         // B fragments: u (K = rows, N = weight columns) and delta2 (N = outputs i), split in registers
         uint32_t uh[NT1][2], ul[NT1][2], eh[NT2][2], el[NT2][2];
 #pragma unroll
         for (int j = 0; j < NT1; ++j) {
-          split_frag(S[blk_off(cU + 8 * j, ra)], uh[j][0], ul[j][0]);
-          split_frag(S[blk_off(cU + 8 * j, rb)], uh[j][1], ul[j][1]);
+          split_frag(S[iU + oa + 256 * j + 4 * r0], uh[j][0], ul[j][0]);
+          split_frag(S[iU + ob + 256 * j + 4 * r0], uh[j][1], ul[j][1]);
         }
 #pragma unroll
         for (int j = 0; j < NT2; ++j) {
-          const float e0 = S[blk_off(cE + 8 * j, ra)], e1 = S[blk_off(cE + 8 * j, rb)];
+          const float e0 = S[iE + oa + 256 * j + 4 * r0], e1 = S[iE + ob + 256 * j + 4 * r0];
           if (sums_b2) db2[j] += e0 + e1;
           split_frag(e0, eh[j][0], el[j][0]);
           split_frag(e1, eh[j][1], el[j][1]);
         }
-        // A fragments: delta1^T (dW1) and h^T (dW2^T)
+        // A fragments: h^T (dW2^T) and delta1^T = (dh * act'(h))^T (dW1)
         uint32_t ah[4], al[4], hh[4], hl[4];
-        const float d0 = S[blk_off(cD, ra)], d1 = S[blk_off(cD + 8, ra)], d2 = S[blk_off(cD, rb)], d3 = S[blk_off(cD + 8, rb)];
+        const float h0 = S[iH + oa + 4 * r0], h1 = S[iH + oa + 256 + 4 * r0], h2 = S[iH + ob + 4 * r0], h3 = S[iH + ob + 256 + 4 * r0];
+        float d0 = dm[0] + dc[0], d1 = dm[2] + dc[2], d2 = dm[1] + dc[1], d3 = dm[3] + dc[3];
+        if (is_tanh) {
+          d0 *= fmaf(-h0, h0, 1.0f); d1 *= fmaf(-h1, h1, 1.0f); d2 *= fmaf(-h2, h2, 1.0f); d3 *= fmaf(-h3, h3, 1.0f);
+        } else {
+          d0 = h0 > 0.f ? d0 : 0.f; d1 = h1 > 0.f ? d1 : 0.f; d2 = h2 > 0.f ? d2 : 0.f; d3 = h3 > 0.f ? d3 : 0.f;
+        }
         db1a += d0 + d2;
         db1b += d1 + d3;
         split_frag(d0, ah[0], al[0]);
         split_frag(d1, ah[1], al[1]);
         split_frag(d2, ah[2], al[2]);
         split_frag(d3, ah[3], al[3]);
-        split_frag(S[blk_off(cH, ra)], hh[0], hl[0]);
-        split_frag(S[blk_off(cH + 8, ra)], hh[1], hl[1]);
-        split_frag(S[blk_off(cH, rb)], hh[2], hl[2]);
-        split_frag(S[blk_off(cH + 8, rb)], hh[3], hl[3]);
+        split_frag(h0, hh[0], hl[0]);
+        split_frag(h1, hh[1], hl[1]);
+        split_frag(h2, hh[2], hl[2]);
+        split_frag(h3, hh[3], hl[3]);
         // independent accumulators are interleaved so that no two consecutive MMAs depend on each other
 #pragma unroll
         for (int j = 0; j < NT1; ++j) mma_1688(c1c[j], al, uh[j][0], uh[j][1]);
@@ -219,8 +268,7 @@ cudaError_t launch_nt2(int NT2, const RnvpWgradArgs& a, int grid, size_t smem, c
     k<<<grid, WG_THREADS, smem, st>>>(a);                                                                \
     return cudaGetLastError();                                                                           \
   }
-  if (NT2 == 2) RNVP_WG_LAUNCH(2)
-  if (NT2 == 4) RNVP_WG_LAUNCH(4)
+  if (NT2 == 2) RNVP_WG_LAUNCH(2)       // D = 32 flows (the tcgen05 backward sweep that feeds this kernel supports only those)
 #undef RNVP_WG_LAUNCH
   return cudaErrorInvalidValue;
 }

@@ -9,9 +9,11 @@ struct RnvpWgradLayer {            // where one layer's gradients live in the pa
 };
 
 struct RnvpWgradArgs {
-  const float* gR;                 // records [L][Npad/32][rec/4][32][4]: delta1 (2H) | h (2H) | u (K1P) | delta2 (2*TP)
+  const float* gR;                 // records [L][Npad/32][rec/4][32][4]: h (2H) | u (K1P) | delta2 (2*TP)
   int rec;                         // floats per record (multiple of 8)
   float* gpacked;
+  const float* packed;             // packed parameters (tile layout, same offsets as gpacked): W2 for the delta1 recompute
+  int act;                         // 1 tanh, 2 relu
   const RnvpWgradLayer* layers;    // device array, L entries
   long long Npad;                  // rows, multiple of 32; padding rows hold zeros in delta1 / delta2
   int n_slices;                    // row slices per layer; grid = L * n_slices
