@@ -235,6 +235,28 @@ def main():
         dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = float(ms)
+
+    # ---- tcgen05 fit path: rnvp_backward = rnvp_mma_kernel<..,2> (forward + backward sweeps) + rnvp_wgrad_kernel.
+    # Time the weight-gradient sweep alone on the records the last step left in the workspace (it accumulates into the
+    # gradient buffer, which is re-zeroed afterwards); the tcgen05 kernel's share is the difference.
+    wgrad_ms = None
+    if eng.fit_on_tensor_cores:
+        import ctypes as ct
+        npad = (per_gpu + 255) // 256 * 256
+        ws = eng.workspace(per_gpu)
+        rec_off = per_gpu * L * D                      # floats of the forward stash that precedes the records
+        rec_ptr = ct.c_void_p(ws.data_ptr() + 4 * rec_off)
+        wa, wb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rc = 0
+        wa.record()
+        for _ in range(K):
+            rc |= eng.lib.rnvp_wgrad_sweep(eng._desc, ct.c_void_p(eng.packed.data_ptr()), npad, rec_ptr,
+                                           ct.c_void_p(eng.gpacked.data_ptr()), None)
+        wb.record()
+        torch.cuda.synchronize()
+        if rc == 0:
+            wgrad_ms = wa.elapsed_time(wb) / K
+        eng.zero_grads()
     rows_per_s = n_global * K / (total_ms * 1e-3)
     final_loss = float(losses[W + K - 1])
 
@@ -333,17 +355,36 @@ def main():
                        "final_loss": final_loss},
             "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak, "traffic": None,
-                         "kernel": ("rnvp_mma_kernel<..,2> (tcgen05 forward sweep) + rnvp_tile_kernel<TR,3> (FP32 backward sweep)"
+                         "kernel": ("rnvp_mma_kernel<..,2> (tcgen05 TF32x3 forward + backward sweeps) + rnvp_wgrad_kernel "
+                                    "(mma.sync TF32x3 weight-gradient sweep), timed together"
+                                    if eng.fit_on_tensor_cores else
+                                    "rnvp_mma_kernel<..,2> (tcgen05 forward sweep) + rnvp_tile_kernel<TR,3> (FP32 backward sweep)"
                                     if eng._bwd_two_kernels else "rnvp_tile_kernel<TR,2> (fused forward+backward)"),
                          "kernel_ms": kms,
                          "kernel_share_of_step": kms / (total_ms / K),
                          "flops_per_row": f_fit, "rows_per_launch": per_gpu,
-                         "peak_source": f"2*128 lanes*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
-                                        "tensor/HBM peaks do not bind this FP32-FMA kernel",
+                         "peak_source": f"FP32-FMA pipe: 2*128 lanes*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz) -- "
+                                        "the roofline of the reference's arithmetic type; the TF32x3 tensor-core kernels spend 3 "
+                                        "MMA flops per algorithmic flop and are bound by tcgen05.mma issue + the tanh epilogue (DESIGN.md 4)",
                          "hbm_gbs": per_gpu * bytes_row / (kms * 1e-3) / 1e9,
                          "hbm_frac_of_measured": per_gpu * bytes_row / (kms * 1e-3) / 1e9 / hbm_peak},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if wgrad_ms is not None:
+            f_wgrad = sum(2 * (2 * H * ((D - (i & 1) + 1) // 2) + 2 * H * (D - (D - (i & 1) + 1) // 2 + Cd)) for i in range(L))
+            rec_bytes = npad * L * eng.lib.rnvp_wgrad_record_floats(eng._desc) * 4
+            line["roofline"]["kernels"] = {
+                "rnvp_mma_kernel<16,8,32,0,1,2>": {
+                    "ms": kms - wgrad_ms, "algorithmic_flops_per_row": f_fit - f_wgrad,
+                    "tflops": per_gpu * (f_fit - f_wgrad) / ((kms - wgrad_ms) * 1e-3) / 1e12,
+                    "hbm_bytes_per_launch": per_gpu * bytes_row + per_gpu * L * D * 8 + rec_bytes,
+                    "note": "forward sweep + backward sweep (recompute, dgrad); writes the activation records"},
+                "rnvp_wgrad_kernel<3,2>": {
+                    "ms": wgrad_ms, "algorithmic_flops_per_row": f_wgrad,
+                    "tflops": per_gpu * f_wgrad / (wgrad_ms * 1e-3) / 1e12,
+                    "hbm_bytes_per_launch": rec_bytes, "hbm_gbs": rec_bytes / (wgrad_ms * 1e-3) / 1e9,
+                    "hbm_frac_of_measured": rec_bytes / (wgrad_ms * 1e-3) / 1e9 / hbm_peak,
+                    "note": "timed alone on the last step's records"}}
         mufu_peak = 16 * sms * sm_max * 1e6                             # MUFU lanes/s: the tanh (ex2 + rcp) pipe
         n_tanh = 2 * H * L
         line["phases"] = {

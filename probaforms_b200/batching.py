@@ -6,13 +6,13 @@ Kept separate from the CUDA plumbing so that the data-parallel arithmetic can be
 import torch
 
 
-def epoch_permutation(n, group=None, device=None):
-    """Row order of one epoch, consuming the global torch RNG exactly as the reference's fresh
+def epoch_seed(group=None, device=None):
+    """The sampler seed of one epoch, consuming the global torch RNG exactly as the reference's fresh
     ``DataLoader(dataset, batch_size, shuffle=True)`` does (realnvp.py:237): one int64 draw for the
     loader's base seed (torch/utils/data/dataloader.py ``_BaseDataLoaderIter.__init__``), one for
-    the ``RandomSampler`` seed (sampler.py ``RandomSampler.__iter__``), then ``randperm(n)`` from a
-    generator seeded with the latter.  With a process group the sampler seed of rank 0 is
-    broadcast so every rank walks the same order (ranks may hold different RNG states)."""
+    the ``RandomSampler`` seed (sampler.py ``RandomSampler.__iter__``).  With a process group the
+    sampler seed of rank 0 is broadcast so every rank walks the same order (ranks may hold different
+    RNG states).  Must be called on the thread that owns the training loop, once per epoch, in order."""
     torch.empty((), dtype=torch.int64).random_()
     seed = torch.empty((), dtype=torch.int64).random_()
     if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -20,9 +20,61 @@ def epoch_permutation(n, group=None, device=None):
         s = seed.reshape(1).to(device) if device is not None else seed.reshape(1)
         torch.distributed.broadcast(s, src=0, group=group)
         seed = s.cpu().reshape(())
+    return int(seed.item())
+
+
+def permutation_from_seed(seed, n):
+    """``randperm(n)`` from a private generator seeded like ``RandomSampler`` does: the reference's row order.
+    Touches no global state, so it may run on a helper thread (torch releases the GIL inside)."""
     g = torch.Generator()
-    g.manual_seed(int(seed.item()))
+    g.manual_seed(seed)
     return torch.randperm(n, generator=g)
+
+
+def epoch_permutation(n, group=None, device=None):
+    """Row order of one epoch = ``permutation_from_seed(epoch_seed(), n)``."""
+    return permutation_from_seed(epoch_seed(group, device), n)
+
+
+class PermutationPrefetcher:
+    """Epoch row orders computed one epoch ahead on a helper thread.
+
+    The sequential Fisher-Yates shuffle behind ``torch.randperm`` on the CPU (tens of ns per row) would otherwise
+    sit on the critical path between epochs; here the order of epoch e+1 is produced while the GPU runs epoch e
+    (and the order of epoch 0 while the rows are uploaded).  Seeds are drawn on the caller's thread, one per epoch
+    that will actually run, in order -- the global RNG is consumed exactly as by the reference's loop.
+    """
+
+    def __init__(self, n, n_epochs, group=None, device=None):
+        import threading
+        self._threading = threading
+        self.n, self.left, self.group, self.device = n, n_epochs, group, device
+        self._thread, self._out = None, None
+        self._launch()
+
+    def _launch(self):
+        if self.left <= 0:
+            self._thread = None
+            return
+        self.left -= 1
+        seed = epoch_seed(self.group, self.device)
+        out = {}
+
+        def work():
+            out["perm"] = permutation_from_seed(seed, self.n)
+
+        self._out = out
+        self._thread = self._threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def next(self):
+        """Row order of the next epoch; starts computing the one after it."""
+        if self._thread is None:
+            raise RuntimeError("PermutationPrefetcher: no epochs left")
+        self._thread.join()
+        perm = self._out["perm"]
+        self._launch()
+        return perm
 
 
 def batch_bounds(n, batch_size):

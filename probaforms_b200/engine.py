@@ -66,6 +66,13 @@ class FlowEngine:
         self.launches = 0                                 # kernels launched through this engine
         self._bwd_two_kernels = self.plan_info(2)["kernel_family"] == 2
 
+    @property
+    def fit_on_tensor_cores(self):
+        """True when rnvp_backward runs rnvp_mma_kernel<..,2> (tcgen05 forward + backward sweeps) followed by
+        rnvp_wgrad_kernel: tcgen05-eligible flows with D = 32 and one hidden layer of width <= 128 (multiple of 16)."""
+        return (self._bwd_two_kernels and self.D == 32 and len(self.hidden) == 1 and self.hidden[0] <= 128
+                and self.hidden[0] % 16 == 0)
+
     def __del__(self):
         try:
             if getattr(self, "_desc", None) is not None and self._desc.value:
@@ -173,7 +180,8 @@ class FlowEngine:
                                               C.c_float(scale), _ptr(self.gpacked), _ptr(self.loss_slot),
                                               _ptr(logp_rows), _ptr(ws), ws.numel() * 4, self._stream()),
                        "rnvp_backward")
-        # tcgen05 path: tensor-core forward sweep + FP32 backward-only sweep = two kernels
+        # tcgen05 path: two kernels (forward[+backward] sweep on the tensor cores, then the FP32 backward sweep or the
+        # weight-gradient sweep)
         self.launches += 2 if self._bwd_two_kernels else 1
 
     def unpack_grads(self, out=None):

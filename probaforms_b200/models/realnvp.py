@@ -21,7 +21,7 @@ import torch.nn as nn
 from .interfaces import GenModel
 from .nflow import InvertibleLayer, NormalizingFlow
 from ..engine import FlowEngine
-from ..batching import epoch_permutation, batch_bounds, shard_bounds
+from ..batching import PermutationPrefetcher, batch_bounds, shard_bounds
 
 
 def _default_device():
@@ -217,7 +217,9 @@ class RealNVP(GenModel):
     def _to_device(A, dev):
         """numpy/torch -> contiguous float32 rows on the device (realnvp.py:226-228)."""
         if isinstance(A, torch.Tensor):
-            return A.to(device=dev, dtype=torch.float32).contiguous()
+            # pinned host tensors upload asynchronously (the epoch's row order is computed meanwhile)
+            nb = A.device.type == "cpu" and A.is_pinned()
+            return A.to(device=dev, dtype=torch.float32, non_blocking=nb).contiguous()
         A = np.asarray(A)
         if A.dtype != np.float32:
             A = A.astype(np.float32)
@@ -240,15 +242,17 @@ class RealNVP(GenModel):
         """
         self._model_init(X, C)
         dev = self._device
-        Xd = self._to_device(X, dev)
-        Cd = self._to_device(C, dev) if C is not None else None
-        eng = self.nf._fused()
-        n = Xd.shape[0]
-        bs = int(self.batch_size)
-
         dist = torch.distributed
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank() if world > 1 else 0
+        n = X.shape[0]
+        bs = int(self.batch_size)
+        # identical row order on every rank (the sampler seed of rank 0 is broadcast); computed one epoch ahead on a
+        # helper thread, the first one while the rows are uploaded
+        perms = PermutationPrefetcher(n, self.n_epochs, device=dev if world > 1 else None)
+        Xd = self._to_device(X, dev)
+        Cd = self._to_device(C, dev) if C is not None else None
+        eng = self.nf._fused()
 
         epochs = range(self.n_epochs)
         bar = None
@@ -258,8 +262,7 @@ class RealNVP(GenModel):
             epochs = bar
         eng.zero_grads()
         for _ in epochs:
-            # identical order on every rank: the sampler seed of rank 0 is broadcast
-            perm = epoch_permutation(n, device=dev if world > 1 else None).to(dev, non_blocking=True)
+            perm = perms.next().to(dev, non_blocking=True)
             bounds = batch_bounds(n, bs)
             losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
             for s, (b0, nb) in enumerate(bounds):           # last partial batch is kept (drop_last=False)
