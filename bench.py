@@ -244,7 +244,7 @@ def main():
         import ctypes as ct
         npad = (per_gpu + 255) // 256 * 256
         ws = eng.workspace(per_gpu)
-        rec_off = per_gpu * L * D                      # floats of the forward stash that precedes the records
+        rec_off = npad * L * D                         # floats of the forward stash that precedes the records
         rec_ptr = ct.c_void_p(ws.data_ptr() + 4 * rec_off)
         wa, wb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         rc = 0

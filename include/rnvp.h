@@ -126,8 +126,8 @@ int rnvp_wgrad_sweep(const rnvp_desc* d, const float* d_packed, int64_t Npad, co
  * only, 2 = same as auto.  rnvp_plan_info reports the family chosen (0 tile, 1 small-flow, 2 tcgen05). */
 int rnvp_set_path(rnvp_desc* d, int path);
 
-/* Development aid: when d_buf (device, 3*2048*2 int64) is non-null, CTA 0 of the tcgen05 fit kernel logs (tag, clock64)
- * pairs of its backward sweep (tile-0 epilogue, tile-1 epilogue, MMA issuer); tools/trace_mma.py prints the timeline. */
+/* Development aid: when d_buf (device, 4*2048*2 int64) is non-null, CTA 0 of the tcgen05 fit kernel logs (tag, clock64)
+ * pairs of its backward sweep (tile-0 epilogue, tile-1 epilogue, and their two MMA issuers); tools/trace_mma.py prints the timeline. */
 int rnvp_debug_set_trace(void* d_buf);
 
 /* Tensor-core primitive self-test (tcgen05.mma kind::tf32, A in TMEM, B in shared memory):

@@ -15,6 +15,7 @@
 
 #include "../../include/rnvp.h"
 #include "rnvp_plan.h"
+#include <cstdlib>
 #include "rnvp_planner.h"
 #include "rnvp_small.h"
 #include "rnvp_mma.h"
@@ -386,7 +387,7 @@ int64_t rnvp_workspace_bytes(const rnvp_desc* dc, int64_t N) {
   if (!d) return -1;
   if (use_mma_bwd(d)) {
     const int64_t n = std::max<int64_t>(N, 1), npad = (n + 255) / 256 * 256;
-    return (n * d->L * 2 * d->mDH + (int64_t)d->L * npad * wgrad_rec_floats(d)) * 4;
+    return (npad * d->L * 2 * d->mDH + (int64_t)d->L * npad * wgrad_rec_floats(d)) * 4;
   }
   if (use_mma(d)) return std::max<int64_t>(N, 1) * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
   Program* p = nullptr;
@@ -498,7 +499,7 @@ int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, 
   if (use_mma_bwd(d) && N > 0) {
     // forward + backward sweeps in one tcgen05 launch (per-layer records to the workspace), then the weight-gradient sweep
     const int64_t npad = (N + 255) / 256 * 256;
-    const int64_t stash_f = (int64_t)N * d->L * 2 * d->mDH, rec_f = (int64_t)d->L * npad * wgrad_rec_floats(d);
+    const int64_t stash_f = npad * d->L * 2 * d->mDH, rec_f = (int64_t)d->L * npad * wgrad_rec_floats(d);   // both blocked by 32 rows
     if (!d_workspace || workspace_bytes < (stash_f + rec_f) * 4)
       return fail(RNVP_EINVAL, "rnvp_backward: workspace too small (see rnvp_workspace_bytes)");
     float* stash = (float*)d_workspace;

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(const float* __res
 }
 
 // ============================================================ fused forward / inverse kernel
-constexpr int MMA_THREADS = 320;
+constexpr int MMA_THREADS = 352;        // warp 0 TMA producer, warp 1 / warp 10 MMA issuers of tile 0 / 1, warps 2-9 epilogue
 
 template <int ACT>
 __device__ __forceinline__ float act_mma(float v) {
@@ -126,13 +126,24 @@ __device__ __forceinline__ float act_mma(float v) {
   return fmaxf(v, 0.0f);
 }
 
-// trace slot `who` (0 / 1: epilogue group of tile 0 / 1, 2: MMA issuer) of CTA 0: (tag, clock64), 2048 events per slot
+// trace slot `who` (0 / 1: epilogue group of tile 0 / 1, 2 / 3: their MMA issuers) of CTA 0: (tag, clock64), 2048 events per slot
 __device__ __forceinline__ void trace_ev(const RnvpMmaArgs& a, int who, int& n, int tag) {
   if (a.trace && blockIdx.x == 0 && n < 2048) {
     a.trace[(who * 2048 + n) * 2] = tag;
     a.trace[(who * 2048 + n) * 2 + 1] = clock64();
     ++n;
   }
+}
+
+// exp(x) = 2^(x*log2e) on the MUFU with the argument's rounding error compensated: t = rn(x*log2e), r = x*log2e - t
+// (exact residual through FMA + the low part of log2e), exp = ex2(t)*(1 + r*ln2).  ~2 ulp, 6 instructions; expf() costs
+// ~25 and sat on the critical path of every coupling layer (16 per row and layer, forward and backward).
+__device__ __forceinline__ float exp_mma(float x) {
+  const float t = x * 1.4426950216293335f;                                   // log2e rounded to fp32
+  const float r = fmaf(x, 1.9259629911266175e-8f, fmaf(x, 1.4426950216293335f, -t));   // + x * (log2e - fp32(log2e))
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return fmaf(e, r * 0.6931471805599453f, e);
 }
 
 enum { B_W1F = 0, B_W1E, B_W2F, B_W2E, B_UF0, B_UF1, B_D1F0, B_D1F1, B_AF0, B_AF1, B_D2F0, B_D2F1, B_COUNT };
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
-    mbar_init(&bars[B_W1F], 1); mbar_init(&bars[B_W1E], 1); mbar_init(&bars[B_W2F], 1); mbar_init(&bars[B_W2E], 1);
+    mbar_init(&bars[B_W1F], 1); mbar_init(&bars[B_W1E], 2); mbar_init(&bars[B_W2F], 1); mbar_init(&bars[B_W2E], 2);   // E: one commit per issuer
     for (int g = 0; g < 2; ++g) {
       mbar_init(&bars[B_UF0 + g], 128); mbar_init(&bars[B_D1F0 + g], 1);
       mbar_init(&bars[B_AF0 + g], 128); mbar_init(&bars[B_D2F0 + g], 1);
@@ -215,11 +226,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             }
           }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 for tile 0, warp 10 for tile 1
+    // (issuing costs ~2x the tensor-pipe time of these small MMAs, so one issuer for both tiles was the bottleneck).
     // The whole warp runs this role (warp-uniform control flow and descriptor arithmetic, so the descriptors
     // live in uniform registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
-    uint32_t ph_w1 = 0, ph_w2 = 0, ph_u[2] = {0, 0}, ph_a[2] = {0, 0};
+    const int g = warp == 1 ? 0 : 1;
+    uint32_t ph_w1 = 0, ph_w2 = 0, ph_u = 0, ph_a = 0;
     const uint32_t idesc1 = idesc_tf32(128, D1W), idesc2 = idesc_tf32(128, NTP);
     const uint32_t lbo = (128u >> 4) << 16;
     const uint32_t w1_lo = ((smem_u32(w1buf) & 0x3FFFFu) >> 4) | lbo, w2_lo = ((smem_u32(w2buf) & 0x3FFFFu) >> 4) | lbo;
@@ -278,33 +291,30 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
     for (int it = 0; it < my_pairs; ++it) {
       for (int li = 0; li < nL; ++li) {
         mbar_wait(&bars[B_W1F], ph_w1); ph_w1 ^= 1;
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&bars[B_UF0 + g], ph_u[g]); ph_u[g] ^= 1;
+        mbar_wait(&bars[B_UF0 + g], ph_u); ph_u ^= 1;
+        fence_after_sync();
+        if (leader) {
+          gemm1(g, 0);
+          if (NCS == 1) mma_commit(&bars[B_W1E]);
+          mma_commit(&bars[B_D1F0 + g]);
+        }
+        __syncwarp();
+        for (int cc = 0; cc < NCS; ++cc) {
+          mbar_wait(&bars[B_AF0 + g], ph_a); ph_a ^= 1;
+          if (cc == 0) { mbar_wait(&bars[B_W2F], ph_w2); ph_w2 ^= 1; }
           fence_after_sync();
           if (leader) {
-            gemm1(g, 0);
-            if (NCS == 1 && g == 1) mma_commit(&bars[B_W1E]);
-            mma_commit(&bars[B_D1F0 + g]);
+            gemm2(g, cc);
+            if (cc + 1 < NCS) {
+              gemm1(g, cc + 1);
+              if (cc + 2 == NCS) mma_commit(&bars[B_W1E]);             // this tile's last GEMM1 of the layer issued
+              mma_commit(&bars[B_D1F0 + g]);
+            }
+            if (cc + 1 == NCS) mma_commit(&bars[B_W2E]);               // this tile's last GEMM2 of the layer issued
+            if (cc + 1 == NCS || (NETSEQ && cc + 1 == NC)) mma_commit(&bars[B_D2F0 + g]);
           }
           __syncwarp();
         }
-        for (int cc = 0; cc < NCS; ++cc)
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(&bars[B_AF0 + g], ph_a[g]); ph_a[g] ^= 1;
-            if (cc == 0 && g == 0) { mbar_wait(&bars[B_W2F], ph_w2); ph_w2 ^= 1; }
-            fence_after_sync();
-            if (leader) {
-              gemm2(g, cc);
-              if (cc + 1 < NCS) {
-                gemm1(g, cc + 1);
-                if (cc + 2 == NCS && g == 1) mma_commit(&bars[B_W1E]);   // last GEMM1 of the layer issued
-                mma_commit(&bars[B_D1F0 + g]);
-              }
-              if (cc + 1 == NCS && g == 1) mma_commit(&bars[B_W2E]);     // last GEMM2 of the layer issued
-              if (cc + 1 == NCS || (NETSEQ && cc + 1 == NC)) mma_commit(&bars[B_D2F0 + g]);
-            }
-            __syncwarp();
-          }
       }
       if constexpr (MODE == 2 && !NETSEQ) {
         if (a.do_bwd) {
@@ -369,37 +379,34 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
           for (int li = 0; li < nL; ++li) {
             mbar_wait(&bars[B_W1F], ph_w1); ph_w1 ^= 1;
             mbar_wait(&bars[B_W2F], ph_w2); ph_w2 ^= 1;
-            if (leader) trace_ev(a, 2, ntr, 200 + li);
-            for (int g = 0; g < 2; ++g) {
-              mbar_wait(&bars[B_UF0 + g], ph_u[g]); ph_u[g] ^= 1;
+            if (leader) trace_ev(a, 2 + g, ntr, 200 + li);
+            mbar_wait(&bars[B_UF0 + g], ph_u); ph_u ^= 1;
+            fence_after_sync();
+            if (leader) {
+              trace_ev(a, 2 + g, ntr, 300);
+              gemmA(g, 0);
+              if (NCB == 1) mma_commit(&bars[B_W2E]);
+              mma_commit(&bars[B_D1F0 + g]);
+            }
+            __syncwarp();
+            for (int hc = 0; hc < NCB; ++hc) {
+              mbar_wait(&bars[B_AF0 + g], ph_a); ph_a ^= 1;
               fence_after_sync();
               if (leader) {
-                trace_ev(a, 2, ntr, 300 + g);
-                gemmA(g, 0);
-                if (NCB == 1 && g == 1) mma_commit(&bars[B_W2E]);
-                mma_commit(&bars[B_D1F0 + g]);
+                trace_ev(a, 2 + g, ntr, 400 + hc);
+                gemmB(g, hc);
+                if (hc + 1 < NCB) {
+                  gemmA(g, hc + 1);
+                  if (hc + 2 == NCB) mma_commit(&bars[B_W2E]);           // this tile's last dh of the layer issued
+                  mma_commit(&bars[B_D1F0 + g]);
+                } else {
+                  mma_commit(&bars[B_W1E]);                              // this tile's last du of the layer issued
+                  mma_commit(&bars[B_D2F0 + g]);
+                }
+                trace_ev(a, 2 + g, ntr, 500 + hc);
               }
               __syncwarp();
             }
-            for (int hc = 0; hc < NCB; ++hc)
-              for (int g = 0; g < 2; ++g) {
-                mbar_wait(&bars[B_AF0 + g], ph_a[g]); ph_a[g] ^= 1;
-                fence_after_sync();
-                if (leader) {
-                  trace_ev(a, 2, ntr, 400 + 2 * hc + g);
-                  gemmB(g, hc);
-                  if (hc + 1 < NCB) {
-                    gemmA(g, hc + 1);
-                    if (hc + 2 == NCB && g == 1) mma_commit(&bars[B_W2E]);   // last dh of the layer issued
-                    mma_commit(&bars[B_D1F0 + g]);
-                  } else {
-                    if (g == 1) mma_commit(&bars[B_W1E]);                    // last du of the layer issued
-                    mma_commit(&bars[B_D2F0 + g]);
-                  }
-                  trace_ev(a, 2, ntr, 500 + 2 * hc + g);
-                }
-                __syncwarp();
-              }
           }
         }
       }
@@ -526,10 +533,24 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             else t = USE_C2 ? __uint_as_float(tv[j]) + __uint_as_float(tc[j]) : __uint_as_float(tv[j]);
             const float s = USE_C2 ? __uint_as_float(sv[j]) + __uint_as_float(sc[j]) : __uint_as_float(sv[j]);
             if (MODE == 2) { sv[j] = __float_as_uint(s); tv[j] = __float_as_uint(xT[e0 + j]); }   // stash s and x_T
-            if (MODE != 1) { xT[e0 + j] = fmaf(xT[e0 + j], expf(s), t); ld += s; }
-            else xT[e0 + j] = (xT[e0 + j] - t) * expf(-s);
+            if (MODE != 1) { xT[e0 + j] = fmaf(xT[e0 + j], exp_mma(s), t); ld += s; }
+            else xT[e0 + j] = (xT[e0 + j] - t) * exp_mma(-s);
           }
-          if (MODE == 2 && valid) {
+          if (MODE == 2 && !NETSEQ && a.do_bwd) {
+            // stash for this kernel's own backward sweep: blocks of 32 rows, [block][layer][float4 group][32 rows][4] --
+            // a warp stores / loads 512 contiguous bytes per instruction (row-major cost 32 L1 wavefronts each);
+            // padding rows are written too (finite values), so the backward sweep reads unconditionally
+            float* sb = a.stash + (((size_t)(row >> 5) * a.L_total + i) * (2 * DH / 4)) * 128 + lane * 4;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              *reinterpret_cast<float4*>(sb + (e0 / 4 + m) * 128) =
+                  make_float4(__uint_as_float(tv[4 * m]), __uint_as_float(tv[4 * m + 1]), __uint_as_float(tv[4 * m + 2]),
+                              __uint_as_float(tv[4 * m + 3]));
+              *reinterpret_cast<float4*>(sb + (DH / 4 + e0 / 4 + m) * 128) =
+                  make_float4(__uint_as_float(sv[4 * m]), __uint_as_float(sv[4 * m + 1]), __uint_as_float(sv[4 * m + 2]),
+                              __uint_as_float(sv[4 * m + 3]));
+            }
+          } else if (MODE == 2 && valid) {    // row-major stash [N][L][x_T | s] for the FP32 backward sweep (rnvp_tile.cu)
             float4* sp = reinterpret_cast<float4*>(a.stash + ((size_t)row * a.L_total + i) * (2 * DH) + e0);
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
@@ -585,8 +606,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 
           int ntr = 0;
           const bool tracer = quarter == 0 && lane == 0;
+
           auto layer_bwd = [&](float (&xT)[DH], float (&xK)[DH], float (&gT)[DH], float (&gK)[DH], int i) {
             if (tracer) trace_ev(a, g, ntr, 100 + i);
+            if (i > a.l0) {       // the next layer's stash block (32 rows x 2*DH floats, contiguous) is needed in ~25 k cycles
+              const float* nx = a.stash + (((size_t)(row >> 5) * a.L_total + (i - 1)) * (2 * DH / 4)) * 128 + lane * 32;
+#pragma unroll
+              for (int q = 0; q < 2 * DH / 32; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + q * 1024));
+            }
             // records: [layer][block of 32 rows][column group of 4][32 slots][4 floats], slot = (row % 32) ^ (group & 1):
             // a warp-level float4 store covers 512 contiguous bytes, and the weight-gradient sweep's mma fragment loads
             // of a block are bank-conflict free (rnvp_wgrad.cu)
@@ -598,17 +625,17 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             // ---- x_T and s of this layer from the forward stash; delta2 and the new g_T
             uint32_t e2h[2 * DH], e2l[2 * DH];
             {
-              const float4* sp = reinterpret_cast<const float4*>(a.stash + ((size_t)row * a.L_total + i) * (2 * DH));
+              const float* sb = a.stash + (((size_t)(row >> 5) * a.L_total + i) * (2 * DH / 4)) * 128 + lane * 4;
 #pragma unroll
               for (int m = 0; m < DH / 4; ++m) {
-                const float4 xv = valid ? sp[m] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 sv = valid ? sp[DH / 4 + m] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 xv = *reinterpret_cast<const float4*>(sb + m * 128);
+                const float4 sv = *reinterpret_cast<const float4*>(sb + (DH / 4 + m) * 128);
                 const float xs4[4] = {xv.x, xv.y, xv.z, xv.w}, ss4[4] = {sv.x, sv.y, sv.z, sv.w};
                 float d2t[4], d2s[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const int e = 4 * m + q;
-                  const float es = expf(ss4[q]);
+                  const float es = exp_mma(ss4[q]);
                   xT[e] = xs4[q];                                   // input of this layer (T half)
                   d2t[q] = gT[e];                                   // dL/dt
                   d2s[q] = fmaf(gT[e] * xs4[q], es, gld);           // dL/ds = g_y*x*exp(s) + g_logdet
@@ -620,6 +647,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                 rec_st(2 * H + K1P8 + DH + 4 * m, make_float4(d2s[0], d2s[1], d2s[2], d2s[3]));
               }
             }
+            if (tracer) trace_ev(a, g, ntr, 3);
 #pragma unroll
             for (int e0 = 0; e0 < 2 * DH; e0 += 8) {
               uint32_t th[8], tl[8];
@@ -644,6 +672,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             for (int m = 0; m < CDMAX / 4; ++m)
               if (DH + 4 * m < K1P8)
                 rec_st(2 * H + DH + 4 * m, make_float4(cc[4 * m], cc[4 * m + 1], cc[4 * m + 2], cc[4 * m + 3]));
+            if (tracer) trace_ev(a, g, ntr, 4);
             tmem_wait_st();
             fence_before_sync();
             mbar_arrive(&bars[B_UF0 + g]);

@@ -10,15 +10,15 @@ eng = nf._fused()
 X = torch.randn(N, D, device=dev); Cn = torch.randn(N, Cd, device=dev)
 eng.zero_grads()
 eng.backward(X, Cn, None, N, -1.0 / N)
-buf = torch.zeros(3 * 2048 * 2, dtype=torch.int64, device=dev)
+buf = torch.zeros(4 * 2048 * 2, dtype=torch.int64, device=dev)
 eng.lib.rnvp_debug_set_trace(C.c_void_p(buf.data_ptr()))
 eng.backward(X, Cn, None, N, -1.0 / N)
 torch.cuda.synchronize()
 eng.lib.rnvp_debug_set_trace(None)
-ev = buf.cpu().view(3, 2048, 2)
-t0 = min(int(ev[w, 0, 1]) for w in range(3) if ev[w, 0, 1] > 0)
+ev = buf.cpu().view(4, 2048, 2)
+t0 = min(int(ev[w, 0, 1]) for w in range(4) if ev[w, 0, 1] > 0)
 rows = []
-for w in range(3):
+for w in range(4):
     for k in range(2048):
         tag, t = int(ev[w, k, 0]), int(ev[w, k, 1])
         if t == 0: break
@@ -30,6 +30,6 @@ lo, hi = starts[4], starts[6]
 prev = {}
 for t, w, tag in rows:
     if lo <= t < hi:
-        print(f"{t - lo:7d}  {'  ' * 12 * w}{['T0', 'T1', 'MMA'][w]} {tag:4d}  (+{t - prev.get(w, t)})")
+        print(f"{t - lo:7d}  {'  ' * 9 * w}{['T0', 'T1', 'MMA0', 'MMA1'][w]} {tag:4d}  (+{t - prev.get(w, t)})")
     prev[w] = t
 print('layer period (clks):', [b - a for a, b in zip(starts[:-1], starts[1:])][:16])
