@@ -7,8 +7,9 @@
 Workload (default ``c3``, BASELINE.json configs[2], the configuration the metric's "fit ... at
 1/2/4/8 B200" is quoted on): RealNVP fit on synthetic N(0,1) rows, D=32, Cd=8, 16 coupling
 layers, hidden (128,), tanh, fp32.  A *step* is one optimisation step of the hot path over one
-batch: fused forward+backward launch, gradient all-reduce (N>1), fused Adam launch
-(reference realnvp.py:246-251).  Weak scaling: 65,536 rows per GPU per step.
+batch: tensor-core forward+backward sweep launch, weight-gradient sweep launch, gradient all-reduce
+(N>1), fused Adam launch (reference realnvp.py:246-251).  Weak scaling: 75,776 rows per GPU per step
+(= 2 row-tile pairs for each of the 148 persistent CTAs; --rows-per-gpu overrides).
 
 value      rows/s, whole job, inputs resident in HBM (a different random batch of a resident
            data set larger than L2 every step -- no L2 flush needed).
@@ -36,7 +37,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (D, Cd, L, hidden, rows per GPU per step, description)
     "c2": (2, 1, 8, (10,), 1 << 20, "configs[1]: 2-D moons flow, 1-D condition, L=8, H=10"),
-    "c3": (32, 8, 16, (128,), 65536, "configs[2]: fit, 32-D rows, 8-D condition, L=16, H=128"),
+    # 75,776 = 148 SMs x 2 pairs of 128-row tiles x 256 rows: every persistent CTA of the tcgen05 fit kernel gets exactly two
+    # row-tile pairs per step (no tail wave; at 65,536 rows 108 of the 148 CTAs get 2 pairs, the other 40 one)
+    "c3": (32, 8, 16, (128,), 75776, "configs[2]: fit, 32-D rows, 8-D condition, L=16, H=128"),
     "c4": (64, 16, 24, (128,), 32768, "configs[3]: 64-D rows, 16-D condition, L=24, H=128 (H assumed)"),
     "c5": (128, 32, 8, (512,), 16384, "configs[4]: 128-D rows, 32-D condition, L=8 (assumed), H=512"),
 }
@@ -175,6 +178,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     K, W = args.steps, max(args.warmup, 3)
@@ -312,7 +316,7 @@ def main():
         Xh = torch.randn(n_e2e, D, generator=hgen).pin_memory()
         Ch = torch.randn(n_e2e, Cd, generator=hgen).pin_memory() if Cd else None
         torch.manual_seed(0)
-        model.fit(Xh[: 2 * n_global], None if Ch is None else Ch[: 2 * n_global])      # warm-up: init + first launches
+        model.fit(Xh, Ch)      # warm-up with the same shapes: lazy init, workspace and pinned staging buffers, first launches
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -126,6 +126,16 @@ int rnvp_wgrad_sweep(const rnvp_desc* d, const float* d_packed, int64_t Npad, co
  * only, 2 = same as auto.  rnvp_plan_info reports the family chosen (0 tile, 1 small-flow, 2 tcgen05). */
 int rnvp_set_path(rnvp_desc* d, int path);
 
+/* Host-side row order of one epoch, produced incrementally (replaces the per-epoch DataLoader(shuffle=True) of
+ * realnvp.py:237: RandomSampler -> torch.randperm(n, generator=Generator().manual_seed(seed)); bit-identical to it).
+ * `out` is a caller-owned HOST buffer of n int64 (pinned memory recommended).  rnvp_perm_advance finalises
+ * out[0 .. upto) and returns the number of final entries, so the first batches can be consumed while a helper thread is
+ * still shuffling the tail.  n must be below 2^32/20 (torch uses another scheme beyond: RNVP_ESHAPE).  No device work. */
+typedef struct rnvp_perm rnvp_perm;
+int rnvp_perm_create(uint64_t seed, int64_t n, int64_t* out, rnvp_perm** p);
+int64_t rnvp_perm_advance(rnvp_perm* p, int64_t upto);
+void rnvp_perm_destroy(rnvp_perm* p);
+
 /* Development aid: when d_buf (device, 4*2048*2 int64) is non-null, CTA 0 of the tcgen05 fit kernel logs (tag, clock64)
  * pairs of its backward sweep (tile-0 epilogue, tile-1 epilogue, and their two MMA issuers); tools/trace_mma.py prints the timeline. */
 int rnvp_debug_set_trace(void* d_buf);

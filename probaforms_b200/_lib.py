@@ -46,6 +46,9 @@ SIGNATURES = {
     "rnvp_wgrad_sweep": (C.c_int, [c_desc_p, c_f32_p, C.c_int64, c_f32_p, c_f32_p, c_stream]),
     "rnvp_set_path": (C.c_int, [c_desc_p, C.c_int]),
     "rnvp_debug_set_trace": (C.c_int, [C.c_void_p]),
+    "rnvp_perm_create": (C.c_int, [C.c_uint64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rnvp_perm_advance": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "rnvp_perm_destroy": (None, [C.c_void_p]),
     "rnvp_mma_selftest": (C.c_int, [c_f32_p, c_f32_p, c_f32_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "rnvp_last_error": (C.c_char_p, []),
     "rnvp_version": (C.c_int, []),

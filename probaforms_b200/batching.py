@@ -36,6 +36,58 @@ def epoch_permutation(n, group=None, device=None):
     return permutation_from_seed(epoch_seed(group, device), n)
 
 
+class StreamingPermutation:
+    """One epoch's row order, shuffled by a helper thread in ``chunk``-row steps through the C ABI
+    (``rnvp_perm_*``, bit-identical to ``torch.randperm`` on the CPU): ``wait(upto)`` returns as soon as the first
+    ``upto`` entries are final, so the fit loop consumes batch k while batch k+1.. are still being shuffled.
+    ``host`` is a (pinned, if CUDA is available) int64 buffer the caller copies slices from."""
+
+    def __init__(self, lib, seed, n, host=None, chunk=16384):
+        import ctypes as C
+        import threading
+        self.n, self.done = n, 0
+        if host is None or host.numel() < n:
+            host = torch.empty(max(n, 1), dtype=torch.int64, pin_memory=torch.cuda.is_available())
+        self.host = host
+        self._cv = threading.Condition()
+        self._err = None
+        handle = C.c_void_p()
+        rc = lib.rnvp_perm_create(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), n, C.c_void_p(host.data_ptr()), C.byref(handle))
+        if rc != 0:
+            raise RuntimeError(f"rnvp_perm_create failed (code {rc})")
+
+        def work():
+            try:
+                done = 0
+                while done < n:
+                    done = int(lib.rnvp_perm_advance(handle, min(n, done + chunk)))     # ctypes drops the GIL
+                    with self._cv:
+                        self.done = done
+                        self._cv.notify_all()
+            except Exception as e:                                                      # pragma: no cover
+                with self._cv:
+                    self._err = e
+                    self._cv.notify_all()
+            finally:
+                lib.rnvp_perm_destroy(handle)
+
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def wait(self, upto):
+        upto = min(upto, self.n)
+        with self._cv:
+            while self.done < upto and self._err is None:
+                self._cv.wait()
+            if self._err is not None:
+                raise self._err
+        return self.host
+
+    def full(self):
+        """The whole order (waits for the helper thread)."""
+        return self.wait(self.n)[: self.n]
+
+
 class PermutationPrefetcher:
     """Epoch row orders computed one epoch ahead on a helper thread.
 
@@ -45,11 +97,16 @@ class PermutationPrefetcher:
     that will actually run, in order -- the global RNG is consumed exactly as by the reference's loop.
     """
 
-    def __init__(self, n, n_epochs, group=None, device=None):
+    def __init__(self, n, n_epochs, group=None, device=None, lib=None, host_buffers=None):
         import threading
         self._threading = threading
         self.n, self.left, self.group, self.device = n, n_epochs, group, device
         self._thread, self._out = None, None
+        # with the native library the order is streamed (StreamingPermutation); two host buffers alternate because the
+        # next epoch is shuffled while the current one is still being consumed
+        self._lib = lib if (lib is not None and n < (2 ** 32 - 1) // 20) else None
+        # (pinned allocations cost ~1 ms/MB: callers that fit repeatedly pass the same two-slot list again)
+        self._bufs, self._flip = host_buffers if host_buffers is not None else [None, None], 0
         self._launch()
 
     def _launch(self):
@@ -58,6 +115,12 @@ class PermutationPrefetcher:
             return
         self.left -= 1
         seed = epoch_seed(self.group, self.device)
+        if self._lib is not None:
+            sp = StreamingPermutation(self._lib, seed, self.n, host=self._bufs[self._flip])
+            self._bufs[self._flip] = sp.host
+            self._flip ^= 1
+            self._out, self._thread = {"stream": sp}, sp._thread
+            return
         out = {}
 
         def work():
@@ -69,12 +132,25 @@ class PermutationPrefetcher:
 
     def next(self):
         """Row order of the next epoch; starts computing the one after it."""
+        return self.next_stream().full() if self._lib is not None else self._next_tensor()
+
+    def _next_tensor(self):
         if self._thread is None:
             raise RuntimeError("PermutationPrefetcher: no epochs left")
         self._thread.join()
         perm = self._out["perm"]
         self._launch()
         return perm
+
+    def next_stream(self):
+        """StreamingPermutation of the next epoch (native library only); starts shuffling the epoch after it."""
+        if self._thread is None:
+            raise RuntimeError("PermutationPrefetcher: no epochs left")
+        if self._lib is None:
+            raise RuntimeError("PermutationPrefetcher: streaming needs the native library")
+        sp = self._out["stream"]
+        self._launch()
+        return sp
 
 
 def batch_bounds(n, batch_size):

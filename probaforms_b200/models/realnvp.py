@@ -190,6 +190,7 @@ class RealNVP(GenModel):
 
         self.loss_history = []
         self._device = None
+        self._perm_host = [None, None]         # pinned staging buffers of the epoch row orders, reused across fits
 
     # ------------------------------------------------------------------ init
     def _model_init(self, X, C):
@@ -249,10 +250,12 @@ class RealNVP(GenModel):
         bs = int(self.batch_size)
         # identical row order on every rank (the sampler seed of rank 0 is broadcast); computed one epoch ahead on a
         # helper thread, the first one while the rows are uploaded
-        perms = PermutationPrefetcher(n, self.n_epochs, device=dev if world > 1 else None)
+        eng = self.nf._fused()
+        perms = PermutationPrefetcher(n, self.n_epochs, device=dev if world > 1 else None, lib=eng.lib,
+                                      host_buffers=self._perm_host)
         Xd = self._to_device(X, dev)
         Cd = self._to_device(C, dev) if C is not None else None
-        eng = self.nf._fused()
+        perm_dev = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
 
         epochs = range(self.n_epochs)
         bar = None
@@ -262,12 +265,16 @@ class RealNVP(GenModel):
             epochs = bar
         eng.zero_grads()
         for _ in epochs:
-            perm = perms.next().to(dev, non_blocking=True)
+            # the epoch's row order streams in from a helper thread (rnvp_perm_*, same order as the reference's
+            # DataLoader): a step only waits for its own batch, the tail of the shuffle overlaps the GPU work
+            stream = perms.next_stream()
             bounds = batch_bounds(n, bs)
             losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
             for s, (b0, nb) in enumerate(bounds):           # last partial batch is kept (drop_last=False)
+                host = stream.wait(b0 + nb)
+                perm_dev[b0:b0 + nb].copy_(host[b0:b0 + nb], non_blocking=True)
                 lo, hi = shard_bounds(b0, nb, rank, world)
-                eng.fit_step(Xd, Cd, perm[lo:hi], hi - lo, nb, self.lr, self.weight_decay,
+                eng.fit_step(Xd, Cd, perm_dev[lo:hi], hi - lo, nb, self.lr, self.weight_decay,
                              losses[s:s + 1], world=world)
             host = losses.cpu()                             # the epoch's only device->host sync
             self.loss_history.extend(host.unbind(0))

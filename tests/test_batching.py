@@ -46,3 +46,32 @@ def test_shards_tile_the_batch():
             cuts = [shard_bounds(10, nb, r, world) for r in range(world)]
             assert cuts[0][0] == 10 and cuts[-1][1] == 10 + nb
             assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+
+
+def test_native_streaming_permutation_is_torch_randperm():
+    """rnvp_perm_* (C ABI, host code) reproduces torch.randperm bit for bit, also when consumed in pieces."""
+    from probaforms_b200 import _lib
+    from probaforms_b200.batching import StreamingPermutation
+    lib = _lib.load()
+    for seed, n in [(0, 1), (1, 2), (12345, 1000), (2 ** 40 + 77, 65537), (2 ** 63 - 1, 300001)]:
+        g = torch.Generator()
+        g.manual_seed(seed)
+        want = torch.randperm(n, generator=g)
+        sp = StreamingPermutation(lib, seed, n, chunk=4099)
+        first = sp.wait(min(n, 10))[: min(n, 10)].clone()          # a prefix is final before the rest
+        assert torch.equal(first, want[: min(n, 10)])
+        assert torch.equal(sp.full(), want)
+
+
+def test_streaming_prefetcher_equals_sequential():
+    from probaforms_b200 import _lib
+    lib = _lib.load()
+    n, epochs = 5000, 3
+    torch.manual_seed(99)
+    want = [epoch_permutation(n) for _ in range(epochs)]
+    tail = torch.rand(2)
+    torch.manual_seed(99)
+    pf = PermutationPrefetcher(n, epochs, lib=lib)
+    got = [pf.next_stream().full().clone() for _ in range(epochs)]
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
+    assert torch.equal(tail, torch.rand(2))
