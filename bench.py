@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--rows-per-gpu", type=int, default=0, help="rows per GPU per step (default per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short c1 / c4 / c5 measurements")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -307,6 +308,55 @@ def main():
     c2_lp, c2_lp_ms, c2_s, c2_s_ms = pass_rates(eng2, X2, C2)
     del X2, C2
 
+    # ---- the other named configurations, one short measurement each (rank-local rows, no communication):
+    # configs[3] (c4) per-row log-density, configs[4] (c5) wide fit step + log-density, configs[0] (c1) README moons fit
+    others = {}
+    if args.workload == "c3" and not args.no_others:
+        for name in ("c4", "c5"):
+            Do, Cdo, Lo, hido, per_o, desco = WORKLOADS[name]
+            torch.manual_seed(0)
+            nfo = NormalizingFlow([RealNVPLayer(Do, Cdo, (torch.arange(Do) + i) % 2, hido, "tanh") for i in range(Lo)],
+                                  prior=None).to(dev)
+            engo = nfo._fused()
+            n_o = per_o * (8 if name == "c4" else 2)
+            Xo = torch.randn(n_o, Do, device=dev, generator=gen)
+            Co = torch.randn(n_o, Cdo, device=dev, generator=gen)
+            o_lp, o_lp_ms, o_s, o_s_ms = pass_rates(engo, Xo, Co)
+            fo_fwd, fo_fit = flops_per_row(Do, Cdo, Lo, hido[0])
+            fam_o = {0: "fp32 tile kernel", 1: "small-flow kernel", 2: "tcgen05 TF32x3 kernel"}[engo.plan_info(0)["kernel_family"]]
+            ent = {"log_prob_rows_s": o_lp, "sample_rows_s": o_s, "rows_per_launch": n_o, "kernel": fam_o,
+                   "flops_per_row_fwd": fo_fwd, "log_prob_tflops": o_lp / world * fo_fwd / 1e12}
+            if name == "c5":
+                engo.zero_grads()
+                r_fit, ms_fit = time_pass(lambda: engo.backward(Xo, Co, None, per_o, -1.0 / per_o), per_o, reps=3)
+                ent.update({"fit_kernel_rows_s": r_fit, "fit_rows_per_launch": per_o, "flops_per_row_fit": fo_fit,
+                            "fit_tflops": r_fit / world * fo_fit / 1e12,
+                            "fit_kernel": "rnvp_tile_kernel<TR,2> (FP32-FMA; no tensor-core path for D=128 / H=512 yet)"})
+            others[name + " -- " + desco] = ent
+            del Xo, Co, engo, nfo
+        if rank == 0:
+            try:
+                from sklearn.datasets import make_moons
+                Xm, ym = make_moons(n_samples=1000, noise=0.1, random_state=0)
+                torch.manual_seed(0)
+                mm = RealNVP(lr=0.01, n_epochs=100)
+                mm.fit(Xm[:64], ym[:64].reshape(-1, 1))                 # lazy init + first launches
+                mm.loss_history.clear()
+                t0 = time.perf_counter()
+                mm.fit(Xm, ym.reshape(-1, 1))
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                Sm = mm.sample(ym.reshape(-1, 1))
+                ds = time.perf_counter() - t0
+                others["c1 -- configs[0]: README make_moons RealNVP(lr=0.01, n_epochs=100), 1000 rows, batch 32"] = {
+                    "fit_wall_s": dt, "steps": len(mm.loss_history), "rows_per_s": 100000 / dt,
+                    "us_per_step": dt / max(len(mm.loss_history), 1) * 1e6, "final_loss": float(mm.loss_history[-1]),
+                    "sample_1000_rows_ms": ds * 1e3, "sample_shape": list(Sm.shape),
+                    "note": "through the public API; launch-bound (3 launches per 32-row step); reference CPU: 43 s (SURVEY 6)"}
+            except Exception as e:                                       # sklearn missing etc.: report, do not fail the bench
+                others["c1"] = {"skipped": repr(e)}
+
     # ---- end to end through the public API with pinned host arrays
     e2e = None
     if not args.no_e2e:
@@ -406,6 +456,7 @@ def main():
             "frac_of_mufu_peak": c2_lp / world * 2 * (2 * hid2[0] * L2) / mufu_peak,
             "frac_of_fp32_fma_peak": c2_lp / world * f2_fwd / 1e12 / fp32_peak,
             "hbm_gbs": c2_lp / world * 16 / 1e9}}
+        line["also"].update(others)
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -83,6 +83,10 @@ class StreamingPermutation:
                 raise self._err
         return self.host
 
+    def available(self):
+        """Number of final entries right now (non-blocking)."""
+        return self.done
+
     def full(self):
         """The whole order (waits for the helper thread)."""
         return self.wait(self.n)[: self.n]

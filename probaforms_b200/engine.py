@@ -63,6 +63,7 @@ class FlowEngine:
         self.exp_avg_sq = None
         self.adam_steps = 0
         self._workspace = None
+        self._ws_rows = 0
         self.launches = 0                                 # kernels launched through this engine
         self._bwd_two_kernels = self.plan_info(2)["kernel_family"] == 2
 
@@ -115,16 +116,20 @@ class FlowEngine:
         """0 auto (tcgen05 TF32x3 kernels where eligible), 1 FP32-FMA kernels only."""
         _lib.check(self.lib.rnvp_set_path(self._desc, int(path)), "rnvp_set_path")
         self._workspace = None
+        self._ws_rows = 0
         self._bwd_two_kernels = self.plan_info(2)["kernel_family"] == 2
 
     def workspace(self, n_rows=1):
         """Scratch for rnvp_backward on a batch of ``n_rows`` rows (grown on demand, never shrunk)."""
+        if self._workspace is not None and n_rows <= self._ws_rows:
+            return self._workspace
         with torch.cuda.device(self.device):
             nbytes = int(self.lib.rnvp_workspace_bytes(self._desc, int(n_rows)))
         if nbytes < 0:
             _lib.check(-1, "rnvp_workspace_bytes")
         if self._workspace is None or self._workspace.numel() * 4 < nbytes:
             self._workspace = torch.empty(max(nbytes, 16) // 4 + 4, dtype=torch.float32, device=self.device)
+        self._ws_rows = max(int(n_rows), getattr(self, "_ws_rows", 0)) if self._workspace.numel() * 4 >= nbytes else 0
         return self._workspace
 
     # ------------------------------------------------------------------ kernels

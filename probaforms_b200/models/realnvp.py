@@ -270,9 +270,13 @@ class RealNVP(GenModel):
             stream = perms.next_stream()
             bounds = batch_bounds(n, bs)
             losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
+            copied = 0
             for s, (b0, nb) in enumerate(bounds):           # last partial batch is kept (drop_last=False)
-                host = stream.wait(b0 + nb)
-                perm_dev[b0:b0 + nb].copy_(host[b0:b0 + nb], non_blocking=True)
+                if copied < b0 + nb:                        # upload whatever is final by now, at least this batch
+                    upto = max(b0 + nb, min(n, stream.available()))
+                    host = stream.wait(upto)
+                    perm_dev[copied:upto].copy_(host[copied:upto], non_blocking=True)
+                    copied = upto
                 lo, hi = shard_bounds(b0, nb, rank, world)
                 eng.fit_step(Xd, Cd, perm_dev[lo:hi], hi - lo, nb, self.lr, self.weight_decay,
                              losses[s:s + 1], world=world)
