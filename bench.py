@@ -334,7 +334,7 @@ def main():
                             "fit_kernel": "rnvp_tile_kernel<TR,2> (FP32-FMA; no tensor-core path for D=128 / H=512 yet)"})
             others[name + " -- " + desco] = ent
             del Xo, Co, engo, nfo
-        if rank == 0:
+        if world == 1:      # single process only: RealNVP.fit under a process group is collective (all ranks would have to join)
             try:
                 from sklearn.datasets import make_moons
                 Xm, ym = make_moons(n_samples=1000, noise=0.1, random_state=0)
