@@ -176,3 +176,21 @@ class NormalizingFlow(nn.Module):
         if C is not None:
             C = torch.as_tensor(C, dtype=torch.float32, device=eng.device)
         return eng.inverse(eps, C)
+
+    def sample_many(self, C, n_draws):
+        """``n_draws`` independent ``sample(C)`` results as one [n_draws, n, D] tensor: the conditions are uploaded and
+        validated once, every draw is one launch into its slice of the output (the notebooks' Monte-Carlo pattern
+        ``for i in range(1000): model.sample(C)``, docs/examples/regression.ipynb cell 13).  Draw k consumes the device
+        generator exactly like the k-th call of ``sample`` would."""
+        if type(C) == type(1):
+            n, C = C, None
+        else:
+            n = len(C)
+        eng = self._fused(repack=False)
+        if C is not None:
+            C = torch.as_tensor(C, dtype=torch.float32, device=eng.device)
+        out = torch.empty(int(n_draws), n, eng.D, dtype=torch.float32, device=eng.device)
+        for k in range(int(n_draws)):
+            eps = torch.randn(n, eng.D, dtype=torch.float32, device=eng.device)
+            eng.inverse(eps, C, out=out[k])
+        return out

@@ -287,10 +287,16 @@ class RealNVP(GenModel):
         self.opt._publish_state(eng)
 
     # ------------------------------------------------------------------ sample
-    def sample(self, C=100):
+    def sample(self, C=100, n_draws=None):
         """Draw rows for the given conditions [n, cond_size], or ``C`` rows if it is a Python int
-        (realnvp.py:265-282).  Returns a float32 numpy array [n, var_size]."""
+        (realnvp.py:265-282).  Returns a float32 numpy array [n, var_size].
+
+        ``n_draws=k`` (additive, not upstream) returns [k, n, var_size]: k independent draws for the same conditions
+        with one upload of ``C`` and one download of the result -- the notebooks' ``for i in range(1000):
+        model.sample(C)`` loop as a single call."""
         if type(C) != type(1):
             C = self._to_device(C, self._device)
+        if n_draws is not None:
+            return self.nf.sample_many(C, n_draws).cpu().detach().numpy()
         X = self.nf.sample(C).cpu().detach().numpy()
         return X

@@ -89,3 +89,59 @@ def test_fit_steps_on_tcgen05_path_track_fp32_path():
         curves[path] = losses.cpu()
     assert float(curves[1][-1]) < float(curves[1][0]) - 1.0          # it does train
     assert torch.allclose(curves[0], curves[1], rtol=1e-4, atol=1e-4), (curves[0], curves[1])
+
+
+def test_wgrad_sweep_through_the_abi_matches_fp64():
+    """rnvp_wgrad_sweep alone (C ABI): blocked records [L][N/32][rec/4][32][4] built on the host side of the ABI, gradients
+    against an fp64 evaluation of dW1 = delta1^T u, dW2 = delta2^T h with delta1 = (delta2 W2) * (1 - h^2)."""
+    import ctypes as C
+    from probaforms_b200 import _lib
+    from probaforms_b200.models import RealNVPLayer, NormalizingFlow
+    dev = torch.device("cuda:0")
+    D, Cd, L, H, N = 32, 8, 3, 64, 2048
+    K1P = (D // 2 + Cd + 7) // 8 * 8
+    torch.manual_seed(0)
+    nf = NormalizingFlow([RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, (H,), "tanh") for i in range(L)], None).to(dev)
+    eng = nf._fused()
+    rec = eng.lib.rnvp_wgrad_record_floats(eng._desc)
+    assert rec == 2 * H + K1P + D
+    g = torch.Generator(device=dev).manual_seed(1)
+    h = torch.tanh(torch.randn(L, N, 2, H, device=dev, generator=g))
+    d2 = torch.randn(L, N, 2, D // 2, device=dev, generator=g)
+    u = torch.randn(L, N, K1P, device=dev, generator=g)
+    u[:, :, D // 2 + Cd:] = 0
+    R = torch.cat([h.reshape(L, N, 2 * H), u, d2.reshape(L, N, D)], dim=2)
+    Rb = R.view(L, N // 32, 32, rec // 4, 4).permute(0, 1, 3, 2, 4).contiguous()
+    Rb[:, :, 1::2] = Rb[:, :, 1::2][:, :, :, torch.arange(32, device=dev) ^ 1]       # slot = row ^ (group & 1)
+    eng.zero_grads()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(eng.lib.rnvp_wgrad_sweep(eng._desc, P(eng.packed), N, P(Rb), P(eng.gpacked), None), "rnvp_wgrad_sweep")
+    torch.cuda.synchronize()
+    gflat = eng.unpack_grads().double()
+    names = [n for n, _ in nf.named_parameters()]
+    spans = dict(zip(names, eng.tensor_spans))
+    sd = {n: p.detach().double() for n, p in nf.named_parameters()}
+    worst = 0.0
+    for i in range(L):
+        par = i & 1
+        xk_cols = list(range(1 - par, D, 2)) + list(range(D, D + Cd))
+        for net, nm in enumerate("ts"):
+            W2 = sd[f"layers.{i}.nn_{nm}.2.weight"][par::2]                        # rows of the transformed features
+            d1 = (d2[i, :, net].double() @ W2) * (1 - h[i, :, net].double() ** 2)
+            want = {f"layers.{i}.nn_{nm}.0.weight": (d1.T @ u[i, :, :D // 2 + Cd].double(), None, xk_cols),
+                    f"layers.{i}.nn_{nm}.0.bias": (d1.sum(0), None, None),
+                    f"layers.{i}.nn_{nm}.2.weight": (d2[i, :, net].double().T @ h[i, :, net].double(), slice(par, None, 2), None),
+                    f"layers.{i}.nn_{nm}.2.bias": (d2[i, :, net].double().sum(0), slice(par, None, 2), None)}
+            for name, (ref, rows, cols) in want.items():
+                off, numel = spans[name]
+                got = gflat[off:off + numel].view(sd[name].shape)
+                if rows is not None:
+                    got = got[rows]
+                if cols is not None:
+                    got = got[:, cols]
+                worst = max(worst, float((got - ref).abs().max() / ref.abs().max()))
+    print("wgrad sweep vs fp64: worst rel", worst)
+    assert worst < 5e-6
+    # argument checks
+    assert eng.lib.rnvp_wgrad_sweep(eng._desc, P(eng.packed), 33, P(Rb), P(eng.gpacked), None) < 0
+    assert eng.lib.rnvp_wgrad_sweep(eng._desc, None, N, P(Rb), P(eng.gpacked), None) < 0

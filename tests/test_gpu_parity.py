@@ -313,3 +313,26 @@ def test_state_dict_roundtrip_and_deepcopy(dev):
             p.mul_(1.5)                                # in-place edits are picked up (re-packed) ...
     assert not torch.equal(nf3.log_prob_rows(X, C), lp)
     assert torch.equal(nf.log_prob_rows(X, C), lp)     # ... and the copy does not alias the original
+
+
+@pytest.mark.gpu
+def test_repeated_sampling_equals_a_loop_of_sample_calls(dev):
+    """sample(C, n_draws=k) (the notebooks' Monte-Carlo loop) == k calls of sample(C) under the same seed."""
+    from probaforms_b200.models import RealNVP
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(200, 5))
+    C = rng.normal(size=(200, 3))
+    torch.manual_seed(0)
+    gen = RealNVP(n_epochs=2)
+    gen.fit(X, C)
+    torch.manual_seed(5)
+    torch.cuda.manual_seed(5)
+    want = np.stack([gen.sample(C) for _ in range(4)])
+    torch.manual_seed(5)
+    torch.cuda.manual_seed(5)
+    got = gen.sample(C, n_draws=4)
+    assert got.shape == (4, 200, 5) and got.dtype == np.float32
+    assert np.array_equal(got, want)
+    gen2 = RealNVP(n_epochs=1)
+    gen2.fit(X, None)
+    assert gen2.sample(7, n_draws=3).shape == (3, 7, 5)
