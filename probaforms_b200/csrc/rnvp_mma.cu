@@ -213,9 +213,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             const float* src = a.wimg + (size_t)i * a.layer_floats;
             const uint32_t wt_bytes = (uint32_t)a.wt_floats * 4u;
             if (step > 0) { mbar_wait(&bars[B_W1E], ph1); ph1 ^= 1; }
-            mbar_expect_tx(&bars[B_W1F], sw ? w1_bytes + wt_bytes : w1_bytes);
-            bulk_g2s(w1buf, src, w1_bytes, &bars[B_W1F]);
-            if (sw) bulk_g2s(w1tbuf, src + a.w1_floats + a.w2_floats + a.wt_floats, wt_bytes, &bars[B_W1F]);
+            if (sw) {       // backward sweep: only the W1T image (nothing is recomputed, the W1 image is not needed)
+              mbar_expect_tx(&bars[B_W1F], wt_bytes);
+              bulk_g2s(w1tbuf, src + a.w1_floats + a.w2_floats + a.wt_floats, wt_bytes, &bars[B_W1F]);
+            } else {
+              mbar_expect_tx(&bars[B_W1F], w1_bytes);
+              bulk_g2s(w1buf, src, w1_bytes, &bars[B_W1F]);
+            }
             if (step > 0) { mbar_wait(&bars[B_W2E], ph2); ph2 ^= 1; }
             if (sw) {       // backward sweep: the W2T image takes the place of the W2 image
               mbar_expect_tx(&bars[B_W2F], wt_bytes);
@@ -319,36 +323,19 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
       if constexpr (MODE == 2 && !NETSEQ) {
         if (a.do_bwd) {
           // ---------------- backward sweep: per half-chunk of 16 units per net
-          //   gemmA: D1B = u W1^T (recompute pre-activations)   and   DHB = delta2 W2   (dh)
-          //   gemmB: DU += delta1 W1[:, x_K columns]                                      (du)
+          //   gemmA: DHB = delta2 W2                       (dh; h itself comes back from the record the forward sweep wrote)
+          //   gemmB: DU += delta1 W1[:, x_K columns]       (du)
           // The transposed products read K-major images of W2^T (in w2buf during this sweep) and W1^T (w1tbuf): per
           // (half-chunk, net) a [16 x 16] block [hi | lo].  (tf32 operands cannot be read MN-major without swizzle.)
           constexpr int D1B = 2 * K1PMAX, DHB = D1B + 32, E2H = DHB + 32, E2L = E2H + 32, DUM = E2L + 32, DUC = DUM + 16;
           static_assert(DUC + 16 <= TILE_COLS, "backward TMEM map must fit the tile");
           static_assert(DH == 16, "transposed images are [16 x 16] blocks");
           const uint32_t idescB = idesc_tf32(128, 16);
-          const uint32_t sbo1_u = (uint32_t)(K1P >> 2) * 8u;                       // W1 image row-group stride, 16 B units
           const uint32_t hit = (512u >> 4) | (1u << 14);                            // [16 x 16] blocks: SBO = 4 core matrices
           const uint32_t w1t_lo = ((smem_u32(w1tbuf) & 0x3FFFFu) >> 4) | lbo;
           const int NCB = H / 16;
           auto gemmA = [&](int g, int hc) {
             const uint32_t tb = tbase + (uint32_t)(g * TILE_COLS);
-            const int c = hc >> 1, hp = hc & 1;
-#pragma unroll
-            for (int net = 0; net < 2; ++net) {
-              const uint32_t grp = (uint32_t)(net * 4 + 2 * hp) * sbo1_u;
-              const uint32_t bh = w1_lo + (uint32_t)(2 * c) * chunk1 + grp, bl = bh + chunk1;
-              const uint32_t dst = tb + D1B + 16 * net;
-#pragma unroll
-              for (int j = 0; j < K1PMAX / 8; ++j)
-                if (j < nk1) mma_tf32_ts(dst, tb + U_LO + 8 * j, desc(bh + 16u * j, hi1), idescB, j ? 1u : 0u);
-#pragma unroll
-              for (int j = 0; j < K1PMAX / 8; ++j)
-                if (j < nk1) mma_tf32_ts(dst, tb + U_HI + 8 * j, desc(bl + 16u * j, hi1), idescB, 1u);
-#pragma unroll
-              for (int j = 0; j < K1PMAX / 8; ++j)
-                if (j < nk1) mma_tf32_ts(dst, tb + U_HI + 8 * j, desc(bh + 16u * j, hi1), idescB, 1u);
-            }
 #pragma unroll
             for (int net = 0; net < 2; ++net) {
               const uint32_t bh = w2_lo + (uint32_t)((hc * 2 + net) * 2) * 64u, bl = bh + 64u;
@@ -446,6 +433,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
         tmem_st_x8(trow + U_LO + DH + e0, lo);
       }
 
+      // activation records of (layer i, this thread's row): [layer][block of 32 rows][column group of 4][32 slots][4 floats],
+      // slot = (row % 32) ^ (group & 1): a warp-level float4 access covers 512 contiguous bytes, and the weight-gradient
+      // sweep's mma fragment loads of a block are bank-conflict free (rnvp_wgrad.cu).  Returns the block's base.
+      auto rec_base = [&](int i) -> float* {
+        return a.records + (((size_t)i * (size_t)(a.Npad >> 5) + (size_t)(row >> 5)) * (size_t)(a.rec >> 2)) * 128;
+      };
       auto layer = [&](float (&xT)[DH], float (&xK)[DH], int i) {
         // ---- u (conditioning half) -> TMEM
 #pragma unroll
@@ -485,10 +478,20 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
               tmem_ld_x32(trow + D1C + q0, r);
               tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float h = act_mma<ACT>(__uint_as_float(r[j]));
-                split_tf32(h, r[j], lo[j]);
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(act_mma<ACT>(__uint_as_float(r[j])));
+              if (MODE == 2 && !NETSEQ && a.do_bwd) {
+                // fit step: h goes to the activation record of (layer, row) now -- the backward sweep and the weight-gradient
+                // sweep read it back instead of recomputing u W1^T and the tanh.  Columns q0.. of a chunk are units
+                // cc*CU.. of net q0/CU (D1 = [nn_t chunk | nn_s chunk]).
+                float* hb = rec_base(i) + (((q0 / CU) * H + cc * CU) >> 2) * 128;
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                  *reinterpret_cast<float4*>(hb + m * 128 + ((lane ^ (m & 1)) << 2)) =
+                      make_float4(__uint_as_float(r[4 * m]), __uint_as_float(r[4 * m + 1]), __uint_as_float(r[4 * m + 2]),
+                                  __uint_as_float(r[4 * m + 3]));
               }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(r[j]), r[j], lo[j]);
               tmem_st_x32(trow + D1C + q0, r);
               tmem_st_x32(trow + A_LO + q0, lo);
             }
@@ -614,10 +617,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 #pragma unroll
               for (int q = 0; q < 2 * DH / 32; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + q * 1024));
             }
-            // records: [layer][block of 32 rows][column group of 4][32 slots][4 floats], slot = (row % 32) ^ (group & 1):
-            // a warp-level float4 store covers 512 contiguous bytes, and the weight-gradient sweep's mma fragment loads
-            // of a block are bank-conflict free (rnvp_wgrad.cu)
-            float* recb = a.records + (((size_t)i * (size_t)(a.Npad >> 5) + (size_t)(rloc >> 5)) * (size_t)(a.rec >> 2)) * 128;
+            float* recb = rec_base(i);
             auto rec_st = [&](int col, float4 v) {
               const int cg = col >> 2;
               *reinterpret_cast<float4*>(recb + cg * 128 + ((lane ^ (cg & 1)) << 2)) = v;
@@ -656,15 +656,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
               tmem_st_x8(trow + E2H + e0, th);
               tmem_st_x8(trow + E2L + e0, tl);
             }
-            // ---- u = [x_K, c, 1] -> TMEM (conditioning half only, the static part is still in place) and record
-#pragma unroll
-            for (int e0 = 0; e0 < DH; e0 += 8) {
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) split_tf32(xK[e0 + j], hi[j], lo[j]);
-              tmem_st_x8(trow + U_HI + e0, hi);
-              tmem_st_x8(trow + U_LO + e0, lo);
-            }
+            // ---- u = [x_K, c] -> record (the weight-gradient sweep needs it; nothing is recomputed here any more)
 #pragma unroll
             for (int m = 0; m < DH / 4; ++m)
               rec_st(2 * H + 4 * m, make_float4(xK[4 * m], xK[4 * m + 1], xK[4 * m + 2], xK[4 * m + 3]));
@@ -679,31 +671,30 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             if (tracer) trace_ev(a, g, ntr, 2);
             // ---- half-chunks: h = act(D1B), delta1 = dh * act'(h); delta1 hi/lo -> TMEM (A operand of du); h, delta1 -> record
             for (int hc = 0; hc < NCB; ++hc) {
-              mbar_wait(&bars[B_D1F0 + g], ph_d1); ph_d1 ^= 1;
-              fence_after_sync();
-              if (tracer) trace_ev(a, g, ntr, 10 + hc);
-              uint32_t pa[32], dh[32];
-              tmem_ld_x32(trow + D1B, pa);
-              tmem_ld_x32(trow + DHB, dh);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float h = act_mma<ACT>(__uint_as_float(pa[j]));
-                const float dp = ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f);
-                const float d1 = __uint_as_float(dh[j]) * dp;
-                pa[j] = __float_as_uint(h);
-                dh[j] = __float_as_uint(d1);
-              }
-              // record: h at [net][unit] (the weight-gradient sweep recomputes delta1 from delta2 and h); this half-chunk
-              // covers units 16hc.. of both nets
+              // h of this half-chunk (units 16hc.. of both nets) from the record the forward sweep wrote: issued before
+              // the wait for dh, so the L2 / HBM latency hides behind the MMAs
+              uint32_t pa_h[32];
 #pragma unroll
               for (int net = 0; net < 2; ++net)
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
-                  const int j = 16 * net + 4 * m;
-                  rec_st(net * H + 16 * hc + 4 * m,
-                         make_float4(__uint_as_float(pa[j]), __uint_as_float(pa[j + 1]), __uint_as_float(pa[j + 2]), __uint_as_float(pa[j + 3])));
+                  const int cg = (net * H + 16 * hc) / 4 + m;
+                  const float4 v = *reinterpret_cast<const float4*>(recb + cg * 128 + ((lane ^ (cg & 1)) << 2));
+                  pa_h[16 * net + 4 * m] = __float_as_uint(v.x); pa_h[16 * net + 4 * m + 1] = __float_as_uint(v.y);
+                  pa_h[16 * net + 4 * m + 2] = __float_as_uint(v.z); pa_h[16 * net + 4 * m + 3] = __float_as_uint(v.w);
                 }
+              mbar_wait(&bars[B_D1F0 + g], ph_d1); ph_d1 ^= 1;
+              fence_after_sync();
+              if (tracer) trace_ev(a, g, ntr, 10 + hc);
+              uint32_t pa[32], dh[32];
+              tmem_ld_x32(trow + DHB, dh);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float h = __uint_as_float(pa_h[j]);
+                const float dp = ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f);
+                dh[j] = __float_as_uint(__uint_as_float(dh[j]) * dp);
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) split_tf32(__uint_as_float(dh[j]), dh[j], pa[j]);     // hi -> dh, lo -> pa
               tmem_st_x32(trow + DHB, dh);
