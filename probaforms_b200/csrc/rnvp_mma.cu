@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
   // in GEMM1 they are issued first (while the accumulator is still tiny), in GEMM2 they get their own accumulator C2
   // (added in the epilogue) whenever the 512 TMEM columns allow it.
   constexpr bool USE_C2 = 2 * (D2C + 2 * D2W) <= 512;
-  constexpr int C2C = D2C + D2W;
+  // GEMM2 accumulators per net: [D2 (NTP) | C2 (NTP)]; concurrent nets: nn_t's pair, then nn_s's pair
+  constexpr int T_D2 = D2C, T_C2 = D2C + NTP, S_D2 = D2C + (NETSEQ ? 0 : 2 * NTP), S_C2 = S_D2 + NTP;
   constexpr int TILE_COLS = D2C + (USE_C2 ? 2 : 1) * D2W;
   static_assert(2 * TILE_COLS <= 512, "two row tiles must fit the 512 TMEM columns");
   static_assert((K1PMAX - DH) % 8 == 0 && DH % 8 == 0, "u is written in 8-column pieces");
@@ -265,31 +266,32 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
       for (int j = 0; j < K1PMAX / 8; ++j)
         if (j < nk1) mma_tf32_ts(tb + D1C, tb + U_HI + 8 * j, desc(bh + 16u * j, hi1), idesc1, 1u);
     };
-    // GEMM2 of chunk step cc of tile g: main products into D2 (seeded with b2), corrections into C2
-    auto gemm2_net = [&](uint32_t tb, int net, int c, uint32_t d2, uint32_t c2, uint32_t ah, uint32_t al) {
-      const uint32_t bh = w2_lo + (uint32_t)((c * 2 + net) * 2) * blk2, bl = bh + blk2;
-      if (c == 0) {     // D2 = 1 * b2 (hi image overwrites, lo image accumulates)
-        mma_tf32_ts(d2, tb + U_HI + k_one, desc(b2_lo + (uint32_t)(net * 2) * blkb, hib), idesc2, 0u);
-        mma_tf32_ts(d2, tb + U_HI + k_one, desc(b2_lo + (uint32_t)(net * 2 + 1) * blkb, hib), idesc2, 1u);
-      }
+    // GEMM2 of chunk step cc of tile g.  Per net the accumulators sit side by side, [D2 | C2] (NTP columns each): main
+    // products into D2 (seeded with b2_hi), split corrections into C2 (seeded with b2_lo).  The hi and lo images of a W2
+    // block (and of b2) are adjacent in shared memory with the same row-group stride, so A_hi x [B_hi ; B_lo] is ONE MMA
+    // of N = 2*NTP that feeds both accumulators: 2 instead of 3 instructions per K step (the issue cost of these small
+    // MMAs, 10 + N/2 cycles, is what bounds the MMA phase).
+    static_assert(USE_C2, "the merged GEMM2 needs the correction accumulator");
+    const uint32_t idesc2m = idesc_tf32(128, 2 * NTP);
+    auto gemm2_net = [&](uint32_t tb, int net, int c, uint32_t d2, uint32_t ah, uint32_t al) {
+      const uint32_t bh = w2_lo + (uint32_t)((c * 2 + net) * 2) * blk2;
+      const uint32_t c2 = d2 + NTP;
+      if (c == 0)       // [D2 | C2] = 1 * [b2_hi ; b2_lo]
+        mma_tf32_ts(d2, tb + U_HI + k_one, desc(b2_lo + (uint32_t)(net * 2) * blkb, hib), idesc2m, 0u);
 #pragma unroll
-      for (int j = 0; j < CU / 8; ++j)
-        mma_tf32_ts(c2, al + 8 * j, desc(bh + 16u * j, hi2), idesc2, (USE_C2 && c == 0 && j == 0) ? 0u : 1u);
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(c2, al + 8 * j, desc(bh + 16u * j, hi2), idesc2, 1u);
 #pragma unroll
-      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(c2, ah + 8 * j, desc(bl + 16u * j, hi2), idesc2, 1u);
-#pragma unroll
-      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(d2, ah + 8 * j, desc(bh + 16u * j, hi2), idesc2, 1u);
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(d2, ah + 8 * j, desc(bh + 16u * j, hi2), idesc2m, 1u);
     };
     auto gemm2 = [&](int g, int cc) {
       const uint32_t tb = tbase + (uint32_t)(g * TILE_COLS);
       if (NETSEQ) {
         const int net = cc >= NC ? 1 : 0;
-        gemm2_net(tb, net, cc - net * NC, tb + D2C, USE_C2 ? tb + C2C : tb + D2C, tb + D1C, tb + A_LO);
+        gemm2_net(tb, net, cc - net * NC, tb + D2C, tb + D1C, tb + A_LO);
       } else {
 #pragma unroll
         for (int net = 0; net < 2; ++net)
-          gemm2_net(tb, net, cc, tb + D2C + net * NTP, USE_C2 ? tb + C2C + net * NTP : tb + D2C + net * NTP,
-                    tb + D1C + net * CU, tb + A_LO + net * CU);
+          gemm2_net(tb, net, cc, tb + D2C + net * 2 * NTP, tb + D1C + net * CU, tb + A_LO + net * CU);
       }
     };
     for (int it = 0; it < my_pairs; ++it) {
@@ -505,8 +507,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 #pragma unroll
             for (int e0 = 0; e0 < DH; e0 += 16) {
               uint32_t tv[16], tc[16];
-              tmem_ld_x16(trow + D2C + e0, tv);
-              if (USE_C2) tmem_ld_x16(trow + C2C + e0, tc);
+              tmem_ld_x16(trow + T_D2 + e0, tv);
+              if (USE_C2) tmem_ld_x16(trow + T_C2 + e0, tc);
               tmem_wait_ld();
 #pragma unroll
               for (int j = 0; j < 16; ++j)
@@ -521,12 +523,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 #pragma unroll
         for (int e0 = 0; e0 < DH; e0 += 16) {
           uint32_t tv[16], sv[16], tc[16], sc[16];
-          constexpr int SOFF = NETSEQ ? 0 : NTP;               // where s sits inside D2 / C2
-          if (!NETSEQ) tmem_ld_x16(trow + D2C + e0, tv);
-          tmem_ld_x16(trow + D2C + SOFF + e0, sv);
+          if (!NETSEQ) tmem_ld_x16(trow + T_D2 + e0, tv);
+          tmem_ld_x16(trow + S_D2 + e0, sv);
           if (USE_C2) {
-            if (!NETSEQ) tmem_ld_x16(trow + C2C + e0, tc);
-            tmem_ld_x16(trow + C2C + SOFF + e0, sc);
+            if (!NETSEQ) tmem_ld_x16(trow + T_C2 + e0, tc);
+            tmem_ld_x16(trow + S_C2 + e0, sc);
           }
           tmem_wait_ld();
 #pragma unroll
