@@ -28,11 +28,13 @@ constexpr int WG_THREADS = WG_WARPS * 32;         // lane 0 of warp 0 doubles as
 constexpr int WG_ROWS = 32;                       // rows per block of the record array = rows per pipeline stage
 constexpr int WG_STAGES = 3;
 
-// A- and B-operand split: hi rounded to TF32, lo = exact fp32 remainder (the tensor core drops its low 13 bits:
-// |error| < 2^-21 |v|, far below the fp32 noise of a 65k-row sum)
+// A- and B-operand split for the 3-pass TF32 products.  mma.sync reads only the upper 19 bits of a tf32 operand, so the
+// fp32 value itself serves as "hi" (the hardware uses trunc(v)) and lo = v - trunc(v) is exact in fp32 (2 instructions per
+// element instead of 3 with a rounded hi; the 16 warps spend more issue slots on splitting than on MMAs).  What is lost is
+// the part of lo below ITS upper 19 bits: < 2^-20 |v| per operand, far below the fp32 noise of a 65k-row sum.
 __device__ __forceinline__ void split_frag(float v, uint32_t& hi, uint32_t& lo) {
-  hi = round_tf32(v);
-  lo = __float_as_uint(v - __uint_as_float(hi));
+  hi = __float_as_uint(v);
+  lo = __float_as_uint(v - __uint_as_float(hi & 0xFFFFE000u));
 }
 __device__ __forceinline__ void mma_1688(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
