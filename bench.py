@@ -179,8 +179,20 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout (one JSON line)
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the communicator is created
+        # (NCCL_DEBUG=VERSION/WARN in the environment), so fd 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     K, W = args.steps, max(args.warmup, 3)
 
