@@ -2,18 +2,24 @@
 // (sampling) passes for flows whose conditioner GEMMs are real contractions (hidden width >= 32,
 // D/2 in {16, 32}: BASELINE configs c3, c4).
 //
-// rnvp_mma_kernel -- one persistent CTA per SM, 10 warps, processes PAIRS of 128-row tiles:
+// rnvp_mma_kernel -- one persistent CTA per SM, 11 warps, processes PAIRS of 128-row tiles:
 //   warp 0      TMA producer: per coupling layer one bulk copy of the W1 image and one of the W2 image
 //               (TF32 hi/lo splits, pre-tiled in the no-swizzle K-major core-matrix layout) into smem
-//   warp 1      MMA issuer (one thread): tcgen05.mma kind::tf32, A operands in TMEM, accumulators in TMEM,
-//               error-compensated 3-pass split (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) = fp32-grade accuracy
+//   warps 1,10  MMA issuers of tile 0 / tile 1 (one elected thread each): tcgen05.mma kind::tf32, A operands in TMEM,
+//               accumulators in TMEM, error-compensated split (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) = fp32-grade accuracy
 //   warps 2-5   epilogue group of tile 0, warps 6-9 of tile 1: ONE THREAD PER ROW.  The row (x, c, log-det)
 //               lives in registers for the whole flow; per layer the thread writes u=[x_K,c,1] to TMEM,
 //               turns each GEMM1 accumulator chunk into tanh(.) hi/lo in place (tcgen05.ld/st), and applies
 //               the coupling y_T = x_T*exp(s)+t from the GEMM2 accumulators.
-//   The two tiles ping-pong: while one tile's threads run the tanh epilogue (MUFU-bound), the tensor core
-//   runs the other tile's MMAs.  Hidden units are processed in chunks of CU per net so that a tile needs
-//   <= 256 TMEM columns (u_hi, u_lo, D1/A_hi, A_lo, D2).  b1 rides in GEMM1 as an extra K column of ones.
+//   While one tile's threads run the tanh epilogue (MUFU-bound), the tensor core runs the other tile's MMAs.
+//   Hidden units are processed in chunks of CU per net so that a tile needs <= 256 TMEM columns
+//   (u_hi, u_lo, D1/A_hi, A_lo, [D2 | C2] per net).  b1 rides in GEMM1 as an extra K column of ones.
+//
+//   MODE 2 (fit step, D = 32 flows): the forward sweep additionally stashes (x_T, s) per layer and writes every
+//   h = act(.) into the activation record of its (layer, row); the same CTA then sweeps the layers BACKWARDS with the
+//   same row ownership: delta2 from the stash -> TMEM, per 16-unit half-chunk dh = delta2 W2 on the tensor core,
+//   delta1 = dh * act'(h) with h read back from the record, du += delta1 W1[:, x_K] (transposed K-major weight
+//   images W2T / W1T).  u and delta2 complete the record; rnvp_wgrad_kernel contracts the records over rows.
 //
 // Also here: the primitive self-test: D[128 x N] = A[128 x K] * B[N x K]^T with A
 // staged in TMEM (tcgen05.st, one thread per row), B in shared memory in the no-swizzle K-major
@@ -670,7 +676,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             fence_before_sync();
             mbar_arrive(&bars[B_UF0 + g]);
             if (tracer) trace_ev(a, g, ntr, 2);
-            // ---- half-chunks: h = act(D1B), delta1 = dh * act'(h); delta1 hi/lo -> TMEM (A operand of du); h, delta1 -> record
+            // ---- half-chunks: delta1 = dh * act'(h) with dh from the MMA warp and h from the record; delta1 hi/lo -> TMEM (A operand of du)
             for (int hc = 0; hc < NCB; ++hc) {
               // h of this half-chunk (units 16hc.. of both nets) from the record the forward sweep wrote: issued before
               // the wait for dh, so the L2 / HBM latency hides behind the MMAs
