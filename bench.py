@@ -373,7 +373,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         model = RealNVP(n_layers=L, hidden=hidden, activation="tanh", batch_size=n_global, n_epochs=1, lr=lr)
-        n_e2e = n_global * max(4, min(K, 16))
+        n_e2e = n_global * max(4, min(K, 16, 32 // world))          # bounded host memory: every rank holds the whole set
         hgen = torch.Generator().manual_seed(7)                      # same host data on every rank
         Xh = torch.randn(n_e2e, D, generator=hgen).pin_memory()
         Ch = torch.randn(n_e2e, Cd, generator=hgen).pin_memory() if Cd else None
@@ -389,9 +389,24 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         steps_e2e = n_e2e // n_global
+        # the same call with the opt-in GPU shuffle (not the reference's batch composition): shows what the sequential
+        # CPU shuffle of the reference-faithful default costs once several GPUs share one global batch
+        model.shuffle = "device"
+        model.fit(Xh, Ch)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.fit(Xh, Ch)
+        torch.cuda.synchronize()
+        dt2 = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
         e2e = {"value": n_e2e / float(dt), "unit": "rows/s",
                "h2d_bytes_per_step": n_global * 4 * (D + Cd) + 8 * n_global, "d2h_bytes_per_step": 4,
-               "steps": steps_e2e, "api": "RealNVP.fit(X_host, C_host), n_epochs=1, replicated data-parallel"}
+               "steps": steps_e2e, "api": "RealNVP.fit(X_host, C_host), n_epochs=1, replicated data-parallel",
+               "shuffle": "reference (default): batches composed exactly as the reference's DataLoader does",
+               "value_with_device_shuffle": n_e2e / float(dt2)}
 
     if rank == 0:
         H = hidden[0]
