@@ -26,6 +26,8 @@ int rnvp_tile_occupancy(int mode, int TR, size_t smem_bytes);
 cudaError_t rnvp_launch_small(int NE, int NC, int act, int mode, const RnvpSmallArgs& a, int grid, size_t smem,
                               cudaStream_t st);
 int rnvp_small_rows_per_block();
+int rnvp_small_fit_rows_per_block();
+int rnvp_small_fit_max_layers();
 cudaError_t rnvp_launch_mma(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st);
 size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats, int w1t_floats);
 cudaError_t rnvp_launch_wgrad(int NT1, int NT2, const RnvpWgradArgs& a, int grid, size_t smem, cudaStream_t st);
@@ -61,6 +63,7 @@ struct rnvp_desc : rnvp_planner::FlowGeom {
   int device = 0, num_sms = 1;
   int* d_p2f = nullptr;   // packed index -> flat index or -1
   int* d_f2p = nullptr;   // flat index -> packed index or -1
+  int* d_s2g = nullptr;   // small-flow layout index -> index in the packed gradient accumulator or -1 (fit step of small flows)
   int* d_f2p2 = nullptr;  // flat index -> index in the small-flow layout or -1 (nullptr if unused)
   int* d_m2f = nullptr;   // tcgen05 region: 4*flat + code (0 hi, 1 lo, 2 full) or -1
   int* d_f2m = nullptr;   // [4*P]: positions of each parameter's TF32 hi / lo images (plain, transposed) in the tcgen05 region, or -1
@@ -227,8 +230,12 @@ int run_tile(rnvp_desc* d, int mode, int l0, int l1, RnvpKArgs& a, void* workspa
   return 0;
 }
 
+// fit step of small flows on the row-per-thread kernel (one launch, no workspace)
+bool use_small_fit(const rnvp_desc* d) { return d->small_ok && d->L <= rnvp_small_fit_max_layers() && d->small_floats * 8 <= d->max_smem; }
+
 int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
-              const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream) {
+              const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream,
+              float* gpacked = nullptr, float* loss_sum = nullptr, float scale = 0.f) {
   if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
   if (N <= 0) return 0;
   RnvpSmallArgs a;
@@ -237,9 +244,10 @@ int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const
   a.out_x = out_x; a.out_logdet = out_logdet; a.out_logp = out_logp;
   a.D = d->D; a.Cd = d->Cd; a.H = d->hidden[0]; a.rec = d->srec; a.small_floats = d->small_floats;
   a.l0 = l0; a.l1 = l1;
-  const long long rpb = rnvp_small_rows_per_block();
+  a.gpacked = gpacked; a.s2g = d->d_s2g; a.loss_sum = loss_sum; a.scale = scale;
+  const long long rpb = mode == 2 ? rnvp_small_fit_rows_per_block() : rnvp_small_rows_per_block();
   const long long blocks = (N + rpb - 1) / rpb;
-  const int grid = (int)std::min<long long>(blocks, (long long)d->num_sms * 8);
+  const int grid = (int)std::min<long long>(blocks, (long long)d->num_sms * (mode == 2 ? 16 : 8));
   cudaError_t e = rnvp_launch_small(d->sNE, d->sNC, d->act, mode, a, grid, (size_t)d->small_floats * 4, stream);
   if (e != cudaSuccess) return cuda_fail(e, "small-flow kernel launch");
   return 0;
@@ -319,7 +327,12 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
   build_maps(d, p2f, f2p);
   build_small_map(d, p2f, f2p2);
   if (d->small_ok) {
-    e = cudaMalloc(&d->d_f2p2, sizeof(int) * f2p2.size());
+    std::vector<int> s2g(d->small_floats, -1);
+    for (size_t f = 0; f < f2p2.size() && f < f2p.size(); ++f)
+      if (f2p2[f] >= 0 && f2p[f] >= 0) s2g[f2p2[f] - d->small_off] = f2p[f];
+    e = cudaMalloc(&d->d_s2g, sizeof(int) * s2g.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d->d_s2g, s2g.data(), sizeof(int) * s2g.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&d->d_f2p2, sizeof(int) * f2p2.size());
     if (e == cudaSuccess) e = cudaMemcpy(d->d_f2p2, f2p2.data(), sizeof(int) * f2p2.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
   }
@@ -372,6 +385,7 @@ void rnvp_desc_destroy(rnvp_desc* d) {
   cudaFree(d->d_p2f);
   cudaFree(d->d_f2p);
   cudaFree(d->d_f2p2);
+  cudaFree(d->d_s2g);
   cudaFree(d->d_m2f);
   cudaFree(d->d_f2m);
   cudaFree(d->d_wg);
@@ -385,6 +399,7 @@ int64_t rnvp_grad_count(const rnvp_desc* d) { return d ? d->packed_tile : -1; }
 int64_t rnvp_workspace_bytes(const rnvp_desc* dc, int64_t N) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
   if (!d) return -1;
+  if (use_small_fit(d)) return 16;                      // the row-per-thread fit kernel keeps its stash in local memory
   if (use_mma_bwd(d)) {
     const int64_t n = std::max<int64_t>(N, 1), npad = (n + 255) / 256 * 256;
     return (npad * d->L * 2 * d->mDH + (int64_t)d->L * npad * wgrad_rec_floats(d)) * 4;
@@ -421,7 +436,7 @@ int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_byte
   if (tile_rows) *tile_rows = 8 * p->TR;
   if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
   if (n_ops) *n_ops = p->n_ops;
-  if (kernel_family) *kernel_family = use_mma(d) ? 2 : ((mode < 2 && d->small_ok) ? 1 : 0);
+  if (kernel_family) *kernel_family = use_mma(d) ? 2 : (((mode < 2 && d->small_ok) || (mode == 2 && use_small_fit(d))) ? 1 : 0);
   return 0;
 }
 
@@ -496,6 +511,9 @@ int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, 
   memset(&a, 0, sizeof(a));
   a.packed = d_packed; a.C = d_C; a.idx = (const long long*)d_idx; a.N = N;
   a.gpacked = d_gpacked; a.scale = scale;
+  if (use_small_fit(d) && N > 0)
+    return run_small(d, 2, 0, d->L, d_packed, d_X, d_C, (const long long*)d_idx, N, nullptr, nullptr, d_logp,
+                     (cudaStream_t)stream, d_gpacked, d_logp_sum, scale);
   if (use_mma_bwd(d) && N > 0) {
     // forward + backward sweeps in one tcgen05 launch (per-layer records to the workspace), then the weight-gradient sweep
     const int64_t npad = (N + 255) / 256 * 256;

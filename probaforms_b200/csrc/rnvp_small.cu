@@ -1,5 +1,5 @@
 // Row-per-thread RealNVP kernels for SMALL flows (README / moons shapes: D<=8, Cd<=4, one hidden
-// layer), forward (log-density) and inverse (sampling).
+// layer): forward (log-density), inverse (sampling) and the fit step (fused forward + backward).
 //
 // For D=2, H=10 a coupling layer is ~120 FMAs per row: tile machinery, barriers and shared-memory
 // round trips would dominate, so here one thread owns RPT whole rows in registers, all coupling
@@ -176,8 +176,209 @@ __global__ void __launch_bounds__(THREADS) rnvp_small_kernel(const RnvpSmallArgs
   }
 }
 
+// ============================================================ fit step for small flows (fused forward + backward)
+//
+// One thread owns one row through the whole flow: forward sweep (stashing x_T and s per layer in local memory), then
+// the backward sweep of d(scale * sum logp)/d(theta) with the hidden activations recomputed per unit (H is ~10).
+// Weight gradients are sums over rows: every per-row contribution is reduced over the warp with shuffles and added by
+// one lane to a shared-memory copy of the gradient (same layout as the weights, private to the CTA's single warp), which
+// is flushed once through the small-layout -> packed-gradient table.  A README-sized step (32 rows, 8 layers, H=10) is
+// one warp of one CTA instead of the ~190 us generic tile program for a single 32-row tile.
+constexpr int FIT_THREADS = 32;    // ONE warp per CTA: the shared-memory gradient copy is private to the warp, so its updates are plain
+                                   // read-modify-writes by the owning lane (a float atomicAdd on shared memory is a CAS spin loop)
+constexpr int FIT_MAXL = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+template <int NE, int NC>
+__device__ __forceinline__ void load_record(const float* __restrict__ u, float (&rv)[2 * NE + NC + 1]) {
+  constexpr int NV = (2 * NE + NC + 1 + 3) / 4;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(u + 4 * q);
+    if (4 * q + 0 < 2 * NE + NC + 1) rv[4 * q + 0] = v.x;
+    if (4 * q + 1 < 2 * NE + NC + 1) rv[4 * q + 1] = v.y;
+    if (4 * q + 2 < 2 * NE + NC + 1) rv[4 * q + 2] = v.z;
+    if (4 * q + 3 < 2 * NE + NC + 1) rv[4 * q + 3] = v.w;
+  }
+}
+
+// forward of one coupling layer for one row (same arithmetic, in the same order, as conditioner_pair + the MODE 0 update)
+template <int NE, int NC, int ACT>
+__device__ __forceinline__ void fit_fwd_layer(const float* __restrict__ wl, int H, int rec, float (&xT)[NE], const float (&xK)[NE],
+                                              const float (&c)[NC > 0 ? NC : 1], float* __restrict__ st_x,
+                                              float* __restrict__ st_s, float& ld) {
+  const int net_floats = H * rec + ((NE + 3) & ~3);
+  float ts[2][NE];
+#pragma unroll
+  for (int net = 0; net < 2; ++net) {
+    const float* w = wl + net * net_floats;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) ts[net][e] = w[H * rec + e];          // b2
+    for (int j = 0; j < H; ++j) {
+      float rv[2 * NE + NC + 1];
+      load_record<NE, NC>(w + j * rec, rv);
+      float a = rv[NE + NC];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xK[e], a);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[k], a);
+      const float h = act_f<ACT>(a);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) ts[net][e] = fmaf(rv[NE + NC + 1 + e], h, ts[net][e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    st_x[e] = xT[e];
+    st_s[e] = ts[1][e];
+    xT[e] = fmaf(xT[e], expf(ts[1][e]), ts[0][e]);
+    ld += ts[1][e];
+  }
+}
+
+// backward of one coupling layer for one row; gl: this layer's slice of the shared-memory gradient accumulator
+template <int NE, int NC, int ACT>
+__device__ __forceinline__ void fit_bwd_layer(const float* __restrict__ wl, float* __restrict__ gl, int H, int rec, float (&xT)[NE],
+                                              const float (&xK)[NE], float (&gT)[NE], float (&gK)[NE],
+                                              const float (&c)[NC > 0 ? NC : 1], const float* __restrict__ st_x,
+                                              const float* __restrict__ st_s, float gld, int lane) {
+  const int net_floats = H * rec + ((NE + 3) & ~3);
+  float d2[2][NE], du[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const float es = expf(st_s[e]);
+    d2[0][e] = gT[e];                                     // dL/dt
+    d2[1][e] = fmaf(gT[e] * st_x[e], es, gld);            // dL/ds = g_y * x * exp(s) + g_logdet
+    gT[e] *= es;                                          // dL/dx_T
+    xT[e] = st_x[e];                                      // input of this layer
+    du[e] = 0.0f;
+  }
+#pragma unroll
+  for (int net = 0; net < 2; ++net) {
+    const float* w = wl + net * net_floats;
+    float* gw = gl + net * net_floats;
+    for (int j = 0; j < H; ++j) {
+      float rv[2 * NE + NC + 1];
+      load_record<NE, NC>(w + j * rec, rv);
+      float a = rv[NE + NC];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xK[e], a);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[k], a);
+      const float h = act_f<ACT>(a);
+      float dh = 0.0f;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) dh = fmaf(d2[net][e], rv[NE + NC + 1 + e], dh);
+      const float d1 = dh * (ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f));
+#pragma unroll
+      for (int e = 0; e < NE; ++e) du[e] = fmaf(d1, rv[e], du[e]);
+      // this row's contribution to the gradient of record j: [w1x | w1c | b1 | w2], reduced over the warp
+      float gv[2 * NE + NC + 1];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) gv[e] = d1 * xK[e];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) gv[NE + k] = d1 * c[k];
+      gv[NE + NC] = d1;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) gv[NE + NC + 1 + e] = d2[net][e] * h;
+#pragma unroll
+      for (int q = 0; q < 2 * NE + NC + 1; ++q) {
+        const float v = warp_sum(gv[q]);
+        if (lane == q) gw[j * rec + q] += v;              // entry q of every record is always updated by lane q
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const float v = warp_sum(d2[net][e]);
+      if (lane == e) gw[H * rec + e] += v;                // b2
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) gK[e] += du[e];
+}
+
+template <int NE, int NC, int ACT>
+__global__ void __launch_bounds__(FIT_THREADS) rnvp_small_fit_kernel(const RnvpSmallArgs a) {
+  extern __shared__ __align__(16) float wsm[];
+  float* gsm = wsm + a.small_floats;
+  const int D = a.D, Cd = a.Cd, H = a.H, rec = a.rec, L = a.l1;
+  for (int i = threadIdx.x * 4; i < a.small_floats; i += FIT_THREADS * 4) {
+    *reinterpret_cast<float4*>(wsm + i) = *reinterpret_cast<const float4*>(a.packed_small + i);
+    *reinterpret_cast<float4*>(gsm + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int layer_floats = 2 * (H * rec + ((NE + 3) & ~3));
+  const int lane = threadIdx.x & 31;
+  float loss_part = 0.0f;
+
+  // every lane of a warp runs the same number of iterations (the shuffles need the full warp); rows >= N carry zeros
+  for (long long base = (long long)blockIdx.x * FIT_THREADS; base < a.N; base += (long long)gridDim.x * FIT_THREADS) {
+    const long long row = base + threadIdx.x;
+    const bool ok = row < a.N;
+    const long long src = ok ? (a.idx ? a.idx[row] : row) : 0;
+    float xe[NE], xo[NE], c[NC > 0 ? NC : 1], ld = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      xe[e] = (ok && 2 * e < D) ? __ldg(a.X + src * D + 2 * e) : 0.0f;
+      xo[e] = (ok && 2 * e + 1 < D) ? __ldg(a.X + src * D + 2 * e + 1) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < (NC > 0 ? NC : 1); ++k) c[k] = (NC > 0 && ok && k < Cd) ? __ldg(a.C + src * Cd + k) : 0.0f;
+
+    float st_x[FIT_MAXL][NE], st_s[FIT_MAXL][NE];        // per-layer stash (local memory, L1-resident)
+    for (int i = 0; i < L; ++i) {
+      const float* wl = wsm + i * layer_floats;
+      if ((i & 1) == 0) fit_fwd_layer<NE, NC, ACT>(wl, H, rec, xe, xo, c, st_x[i], st_s[i], ld);
+      else fit_fwd_layer<NE, NC, ACT>(wl, H, rec, xo, xe, c, st_x[i], st_s[i], ld);
+    }
+    float q = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      q = fmaf(xe[e], xe[e], q);
+      q = fmaf(xo[e], xo[e], q);
+    }
+    const float lp = ld - 0.5f * (D * 1.8378770664093453f + q);
+    if (ok) {
+      if (a.out_logp) a.out_logp[row] = lp;
+      loss_part += lp;
+    }
+    // backward: g_z = -scale * z, g_logdet = scale
+    const float gld = ok ? a.scale : 0.0f;
+    float ge[NE], go[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { ge[e] = -gld * xe[e]; go[e] = -gld * xo[e]; }
+    for (int i = L - 1; i >= 0; --i) {
+      const float* wl = wsm + i * layer_floats;
+      float* gl = gsm + i * layer_floats;
+      if ((i & 1) == 0) fit_bwd_layer<NE, NC, ACT>(wl, gl, H, rec, xe, xo, ge, go, c, st_x[i], st_s[i], gld, lane);
+      else fit_bwd_layer<NE, NC, ACT>(wl, gl, H, rec, xo, xe, go, ge, c, st_x[i], st_s[i], gld, lane);
+    }
+  }
+  if (a.loss_sum) {
+    const float v = warp_sum(loss_part);
+    if (lane == 0 && v != 0.0f) atomicAdd(a.loss_sum, v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.small_floats; i += FIT_THREADS) {
+    const int t = a.s2g[i];
+    const float g = gsm[i];
+    if (t >= 0 && g != 0.0f) atomicAdd(a.gpacked + t, g);
+  }
+}
+
 template <int NE, int NC, int ACT>
 cudaError_t launch_mode(int mode, const RnvpSmallArgs& a, int grid, size_t smem, cudaStream_t st) {
+  if (mode == 2) {
+    auto k = rnvp_small_fit_kernel<NE, NC, ACT>;
+    if (2 * smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+    k<<<grid, FIT_THREADS, 2 * smem, st>>>(a);
+    return cudaGetLastError();
+  }
   if (mode == 0) {
     auto k = rnvp_small_kernel<NE, NC, ACT, 0>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -207,6 +408,8 @@ cudaError_t launch_nc(int NC, int act, int mode, const RnvpSmallArgs& a, int gri
 }  // namespace
 
 int rnvp_small_rows_per_block() { return THREADS * RPT; }
+int rnvp_small_fit_rows_per_block() { return FIT_THREADS; }
+int rnvp_small_fit_max_layers() { return FIT_MAXL; }
 
 cudaError_t rnvp_launch_small(int NE, int NC, int act, int mode, const RnvpSmallArgs& a, int grid, size_t smem,
                               cudaStream_t st) {

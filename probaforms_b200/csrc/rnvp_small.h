@@ -13,4 +13,10 @@ struct RnvpSmallArgs {
   float* out_logp;
   int D, Cd, H, rec, small_floats;
   int l0, l1;
+  // fit step (rnvp_small_fit_kernel): d(scale * sum_rows logp)/d(theta) accumulated into gpacked (tile layout) through
+  // s2g[small index] = gpacked index or -1; loss_sum += sum_rows logp
+  float* gpacked;
+  const int* s2g;
+  float* loss_sum;
+  float scale;
 };

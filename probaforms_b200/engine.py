@@ -19,7 +19,21 @@ def _act_code(activation):
 
 
 def _ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device address of a tensor (or an already computed integer address) as a ctypes pointer."""
+    if t is None:
+        return None
+    return C.c_void_p(t if isinstance(t, int) else t.data_ptr())
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
 
 
 class FlowEngine:
@@ -83,6 +97,13 @@ class FlowEngine:
             pass
 
     # ------------------------------------------------------------------ helpers
+    def _guard(self):
+        """Device guard for a library call; free when the engine's device is already current (the per-step host
+        overhead matters for README-sized batches: two launches per 32-row step)."""
+        if torch.cuda.current_device() == self.device.index:
+            return _NO_GUARD
+        return torch.cuda.device(self.device)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -180,7 +201,7 @@ class FlowEngine:
         if n_rows <= 0:
             return
         ws = self.workspace(n_rows)
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.rnvp_backward(self._desc, _ptr(self.packed), _ptr(X), _ptr(Cn), _ptr(idx), n_rows,
                                               C.c_float(scale), _ptr(self.gpacked), _ptr(self.loss_slot),
                                               _ptr(logp_rows), _ptr(ws), ws.numel() * 4, self._stream()),
@@ -208,7 +229,7 @@ class FlowEngine:
         """One torch.optim.Adam step on the flat parameters + refresh of the packed copy."""
         self._ensure_adam_state()
         self.adam_steps += 1
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self.lib.rnvp_adam_step(
                 self._desc, _ptr(self.flat), _ptr(self.packed), _ptr(self.gpacked), _ptr(gflat_in),
                 _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(gflat_out), C.c_float(grad_scale),
@@ -221,7 +242,8 @@ class FlowEngine:
     def fit_step(self, X, Cn, idx, n_rows, n_global, lr, weight_decay, loss_dst, group=None, world=1):
         """loss=-mean logp over the global batch; backward; (all-reduce); Adam.  2 launches (+1 NCCL).
 
-        ``idx`` selects this rank's rows of the batch, ``n_global`` is the batch size summed over
+        ``idx`` (int64 tensor, or the integer device address of one) selects this rank's rows of the batch;
+        ``loss_dst`` is a 1-element float tensor or its integer device address.  ``n_global`` is the batch size summed over
         ranks (realnvp.py:246-251 with batch_size = n_global).  The accumulator must be zero on
         entry; adam_step(zero=True) leaves it zero again.
         """

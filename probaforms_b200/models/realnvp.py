@@ -277,6 +277,7 @@ class RealNVP(GenModel):
             # DataLoader): a step only waits for its own batch, the tail of the shuffle overlaps the GPU work
             bounds = batch_bounds(n, bs)
             losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
+            loss_ptr = losses.data_ptr()
             if device_shuffle:
                 gen = torch.Generator(device=dev)
                 gen.manual_seed(epoch_seed(device=dev if world > 1 else None) & 0x7FFFFFFFFFFFFFFF)
@@ -284,6 +285,7 @@ class RealNVP(GenModel):
                 stream, copied = None, n
             else:
                 stream, copied = perms.next_stream(), 0
+            perm_ptr = perm_dev.data_ptr()
             for s, (b0, nb) in enumerate(bounds):           # last partial batch is kept (drop_last=False)
                 if copied < b0 + nb:                        # upload whatever is final by now, at least this batch
                     upto = max(b0 + nb, min(n, stream.available()))
@@ -291,8 +293,9 @@ class RealNVP(GenModel):
                     perm_dev[copied:upto].copy_(host[copied:upto], non_blocking=True)
                     copied = upto
                 lo, hi = shard_bounds(b0, nb, rank, world)
-                eng.fit_step(Xd, Cd, perm_dev[lo:hi], hi - lo, nb, self.lr, self.weight_decay,
-                             losses[s:s + 1], world=world)
+                # raw device addresses instead of tensor slices: the host side of a 32-row step is the bottleneck
+                eng.fit_step(Xd, Cd, perm_ptr + 8 * lo, hi - lo, nb, self.lr, self.weight_decay,
+                             loss_ptr + 4 * s, world=world)
             host = losses.cpu()                             # the epoch's only device->host sync
             self.loss_history.extend(host.unbind(0))
             if bar is not None:
