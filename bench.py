@@ -185,7 +185,9 @@ def main():
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            import datetime
+            # a rank that dies or skips a collective must fail the run in minutes, not hang it
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize()
