@@ -453,6 +453,20 @@ def main():
                          "hbm_frac_of_measured": per_gpu * bytes_row / (kms * 1e-3) / 1e9 / hbm_peak},
             "gpu_launches": launches, "clocks": clocks,
         }
+        bf16_sust = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1346.6)
+        if eng.fit_on_tensor_cores:
+            # transparency: what the tensor pipes actually execute (3 TF32 MMA passes per algorithmic MAC, operand padding
+            # not counted) against the dense TF32 rate (half the measured bf16 rate) -- they are far from saturated; and
+            # the DRAM bytes of one step from the committed ncu capture of this command's kernels (activation records)
+            line["roofline"]["tensor_pipe"] = {
+                "executed_tf32_tflops": 3 * achieved, "peak_tf32_tflops": bf16_sust / 2,
+                "frac": 3 * achieved / (bf16_sust / 2),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)"}
+            if per_gpu == 75776 and args.workload == "c3":
+                line["roofline"]["traffic"] = 4.52e9
+                line["roofline"]["traffic_note"] = ("dram__bytes_read+write per step from profiles/r01_g_ncu_full_c3_fit_raw.csv: "
+                                                    "tcgen05 kernel 1.33 + 1.68 GB, weight-gradient sweep 1.51 GB (activation "
+                                                    "records written once, read twice, by design; rows themselves are 12.7 MB)")
         if wgrad_ms is not None:
             f_wgrad = sum(2 * (2 * H * ((D - (i & 1) + 1) // 2) + 2 * H * (D - (D - (i & 1) + 1) // 2 + Cd)) for i in range(L))
             rec_bytes = npad * L * eng.lib.rnvp_wgrad_record_floats(eng._desc) * 4
