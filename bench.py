@@ -404,11 +404,24 @@ def main():
         dt2 = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
+        # sample() end to end: conditions from pinned host memory in, numpy rows out (H2D of C, randn + inverse kernel, D2H)
+        n_smp = min(n_e2e, 1 << 20)
+        model.sample(Ch[:4096] if Ch is not None else 4096)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Xs = model.sample(Ch[:n_smp] if Ch is not None else n_smp)
+        dts = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+        e2e_sample = {"value": n_smp * world / float(dts), "unit": "rows/s", "rows_per_call": n_smp,
+                      "h2d_bytes_per_call": n_smp * 4 * Cd, "d2h_bytes_per_call": int(Xs.nbytes),
+                      "api": "RealNVP.sample(C_host) -> numpy (every rank samples its own rows, no communication)"}
+        del Xs
         e2e = {"value": n_e2e / float(dt), "unit": "rows/s",
                "h2d_bytes_per_step": n_global * 4 * (D + Cd) + 8 * n_global, "d2h_bytes_per_step": 4,
                "steps": steps_e2e, "api": "RealNVP.fit(X_host, C_host), n_epochs=1, replicated data-parallel",
                "shuffle": "reference (default): batches composed exactly as the reference's DataLoader does",
-               "value_with_device_shuffle": n_e2e / float(dt2)}
+               "value_with_device_shuffle": n_e2e / float(dt2), "sample": e2e_sample}
 
     if rank == 0:
         H = hidden[0]
