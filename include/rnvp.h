@@ -86,6 +86,14 @@ int rnvp_forward(const rnvp_desc* d, const float* d_packed, const float* d_X, co
 int rnvp_inverse(const rnvp_desc* d, const float* d_packed, const float* d_Y, const float* d_C,
                  int64_t N, int layer_begin, int layer_end, float* d_X, void* stream);
 
+/* NormalizingFlow.sample in one launch (nflow.py:141-143): the prior draw X = prior.sample((n,)) is generated inside the
+ * inverse kernel instead of being written to and read back from device memory.  Latent element (row, j) is a pure
+ * function of (seed, row_offset + row, j) -- Philox4x32-10 + Box-Muller, csrc/rnvp_philox.cuh -- so a row block gives
+ * the same rows whichever GPU or launch produces it: shard a request of n rows over GPUs by passing each shard its
+ * first global row as row_offset (no communication).  rnvp_inverse stays the parity mode (caller-supplied noise). */
+int rnvp_sample(const rnvp_desc* d, const float* d_packed, const float* d_C, int64_t N, uint64_t seed,
+                int64_t row_offset, float* d_X, void* stream);
+
 /* Fused forward + backward of  out = scale * sum_rows logp(row)  (loss.backward() of
  * loss = -nf.log_prob(X, C), realnvp.py:246-250, is scale = -1/N).  Activations are recomputed,
  * weight gradients are ACCUMULATED into d_gpacked (caller zeroes it), sum_rows logp is
@@ -135,6 +143,15 @@ typedef struct rnvp_perm rnvp_perm;
 int rnvp_perm_create(uint64_t seed, int64_t n, int64_t* out, rnvp_perm** p);
 int64_t rnvp_perm_advance(rnvp_perm* p, int64_t upto);
 void rnvp_perm_destroy(rnvp_perm* p);
+
+/* Host-side ingestion / egress helpers (no device work; HOST pointers).  rnvp_host_gather_rows writes
+ * dst[r][0..width) = (float) src[idx ? idx[r] : row0 + r][0..width) for r in [0, n): the rows of one optimisation step,
+ * converted from the caller's float64 (src_is_f64 != 0) or float32 array -- torch.tensor(X, dtype=float32) of
+ * realnvp.py:226-228 fused with the batch gather of realnvp.py:237 -- into a (pinned) staging buffer, on up to `threads`
+ * host threads.  rnvp_host_copy is a multi-threaded memcpy (the .cpu().numpy() of realnvp.py:281 into a fresh array). */
+int rnvp_host_gather_rows(const void* src, int src_is_f64, int64_t width, const int64_t* idx, int64_t row0, int64_t n,
+                          float* dst, int threads);
+int rnvp_host_copy(void* dst, const void* src, int64_t bytes, int threads);
 
 /* Development aid: when d_buf (device, 4*2048*2 int64) is non-null, CTA 0 of the tcgen05 fit kernel logs (tag, clock64)
  * pairs of its backward sweep (tile-0 epilogue, tile-1 epilogue, and their two MMA issuers); tools/trace_mma.py prints the timeline. */

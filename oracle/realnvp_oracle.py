@@ -177,6 +177,53 @@ def flow_sample(C, var_size, params, n_layers, n_hidden, activation):
 
 
 # --------------------------------------------------------------------------
+# in-kernel prior draws of the product's sampling path (no reference line: upstream calls
+# prior.sample((n,)) == torch.randn on the CPU generator, nflow.py:141).  The CUDA inverse kernels
+# generate the same N(0,1) field from a counter-based generator keyed on the GLOBAL row index
+# (probaforms_b200/csrc/rnvp_philox.cuh); this is its numpy restatement.
+# --------------------------------------------------------------------------
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11; Random123).  counter [..., 4], key [..., 2] uint32 arrays."""
+    import numpy as np
+    c = [np.asarray(counter[..., i], dtype=np.uint64) for i in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint64)
+    k1 = np.asarray(key[..., 1], dtype=np.uint64)
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    for _ in range(10):
+        p0 = c[0] * np.uint64(M0)
+        p1 = c[2] * np.uint64(M1)
+        hi0, lo0 = p0 >> np.uint64(32), p0 & np.uint64(MASK)
+        hi1, lo1 = p1 >> np.uint64(32), p1 & np.uint64(MASK)
+        c = [(hi1 ^ c[1] ^ k0) & np.uint64(MASK), lo1, (hi0 ^ c[3] ^ k1) & np.uint64(MASK), lo0]
+        k0 = (k0 + np.uint64(W0)) & np.uint64(MASK)
+        k1 = (k1 + np.uint64(W1)) & np.uint64(MASK)
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_normal(seed: int, row_offset: int, n: int, var_size: int) -> torch.Tensor:
+    """eps [n, var_size] fp32: element (r, j) from Philox(counter=(row_lo, row_hi, j//4, 0), key=seed) + Box-Muller,
+    u = ((x >> 9) + 0.5) * 2^-23; outputs (0,1) -> features 4q, 4q+1 (cos, sin), (2,3) -> 4q+2, 4q+3."""
+    import numpy as np
+    nq = (var_size + 3) // 4
+    rows = (np.arange(n, dtype=np.uint64) + np.uint64(row_offset))[:, None].repeat(nq, 1)
+    ctr = np.zeros((n, nq, 4), dtype=np.uint64)
+    ctr[..., 0] = rows & np.uint64(0xFFFFFFFF)
+    ctr[..., 1] = rows >> np.uint64(32)
+    ctr[..., 2] = np.arange(nq, dtype=np.uint64)[None, :]
+    key = np.zeros((n, nq, 2), dtype=np.uint64)
+    key[..., 0] = np.uint64(seed & 0xFFFFFFFF)
+    key[..., 1] = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    x = philox4x32_10(ctr, key)
+    u = ((x >> np.uint32(9)).astype(np.float64) + 0.5) * 2.0 ** -23
+    out = np.empty((n, nq, 4), dtype=np.float64)
+    for a, b in ((0, 1), (2, 3)):
+        r = np.sqrt(-2.0 * np.log(u[..., a]))
+        out[..., a] = r * np.cos(2.0 * np.pi * u[..., b])
+        out[..., b] = r * np.sin(2.0 * np.pi * u[..., b])
+    return torch.from_numpy(out.reshape(n, nq * 4)[:, :var_size].astype(np.float32))
+
+
+# --------------------------------------------------------------------------
 # gradients and Adam (reference realnvp.py:205-207, 246-251)
 # --------------------------------------------------------------------------
 def loss_and_grads(X, C, params: Params, n_layers: int, n_hidden: int, activation: str):

@@ -37,6 +37,7 @@ SIGNATURES = {
                                c_f32_p, c_f32_p, c_f32_p, c_stream]),
     "rnvp_inverse": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, c_f32_p, C.c_int64, C.c_int, C.c_int,
                                c_f32_p, c_stream]),
+    "rnvp_sample": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, C.c_int64, C.c_uint64, C.c_int64, c_f32_p, c_stream]),
     "rnvp_backward": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, c_f32_p, c_i64_p, C.c_int64, C.c_float,
                                 c_f32_p, c_f32_p, c_f32_p, C.c_void_p, C.c_int64, c_stream]),
     "rnvp_adam_step": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p,
@@ -49,6 +50,9 @@ SIGNATURES = {
     "rnvp_perm_create": (C.c_int, [C.c_uint64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "rnvp_perm_advance": (C.c_int64, [C.c_void_p, C.c_int64]),
     "rnvp_perm_destroy": (None, [C.c_void_p]),
+    "rnvp_host_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                        C.c_int]),
+    "rnvp_host_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "rnvp_mma_selftest": (C.c_int, [c_f32_p, c_f32_p, c_f32_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "rnvp_last_error": (C.c_char_p, []),
     "rnvp_version": (C.c_int, []),
@@ -57,7 +61,7 @@ SIGNATURES = {
 
 def build(verbose=False):
     """Compile librnvp_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    r = subprocess.run(["make", f"-j{min(os.cpu_count() or 1, 8)}", "-C", CSRC], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building librnvp_b200.so failed:\n" + r.stdout + r.stderr)
     if verbose:

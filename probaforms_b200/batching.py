@@ -109,6 +109,7 @@ class PermutationPrefetcher:
         # with the native library the order is streamed (StreamingPermutation); two host buffers alternate because the
         # next epoch is shuffled while the current one is still being consumed
         self._lib = lib if (lib is not None and n < (2 ** 32 - 1) // 20) else None
+        self.streaming = self._lib is not None     # False: whole-tensor torch.randperm per epoch (next())
         # (pinned allocations cost ~1 ms/MB: callers that fit repeatedly pass the same two-slot list again)
         self._bufs, self._flip = host_buffers if host_buffers is not None else [None, None], 0
         self._launch()

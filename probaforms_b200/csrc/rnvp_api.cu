@@ -235,7 +235,8 @@ bool use_small_fit(const rnvp_desc* d) { return d->small_ok && d->L <= rnvp_smal
 
 int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
               const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream,
-              float* gpacked = nullptr, float* loss_sum = nullptr, float scale = 0.f) {
+              float* gpacked = nullptr, float* loss_sum = nullptr, float scale = 0.f, unsigned long long seed = 0,
+              long long row_offset = 0) {
   if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
   if (N <= 0) return 0;
   RnvpSmallArgs a;
@@ -245,6 +246,7 @@ int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const
   a.D = d->D; a.Cd = d->Cd; a.H = d->hidden[0]; a.rec = d->srec; a.small_floats = d->small_floats;
   a.l0 = l0; a.l1 = l1;
   a.gpacked = gpacked; a.s2g = d->d_s2g; a.loss_sum = loss_sum; a.scale = scale;
+  a.seed = seed; a.row_offset = row_offset;
   const long long rpb = mode == 2 ? rnvp_small_fit_rows_per_block() : rnvp_small_rows_per_block();
   const long long blocks = (N + rpb - 1) / rpb;
   const int grid = (int)std::min<long long>(blocks, (long long)d->num_sms * (mode == 2 ? 16 : 8));
@@ -265,7 +267,8 @@ int wgrad_rec_floats(const rnvp_desc* d) {
 
 int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
             const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream,
-            float* stash = nullptr, float* loss_sum = nullptr, float* records = nullptr, float scale = 0.f) {
+            float* stash = nullptr, float* loss_sum = nullptr, float* records = nullptr, float scale = 0.f,
+            unsigned long long seed = 0, long long row_offset = 0) {
   if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
   if (N <= 0) return 0;
   RnvpMmaArgs a;
@@ -278,6 +281,7 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.do_bwd = records != nullptr; a.scale = scale; a.records = records; a.rec = 0; a.Npad = 0;
   a.wt_floats = records ? d->m_wt_floats : 0;
   a.trace = g_mma_trace;
+  a.seed = seed; a.row_offset = row_offset;
   const long long pairs = (N + 255) / 256;
   if (pairs > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
   a.n_pairs = (int)pairs;
@@ -498,6 +502,24 @@ int rnvp_inverse(const rnvp_desc* dc, const float* d_packed, const float* d_Y, c
   memset(&a, 0, sizeof(a));
   a.packed = d_packed; a.X = d_Y; a.C = d_C; a.N = N; a.out_x = d_X;
   return run_tile(d, 1, layer_begin, layer_end, a, nullptr, 0, (cudaStream_t)stream);
+}
+
+int rnvp_sample(const rnvp_desc* dc, const float* d_packed, const float* d_C, int64_t N, uint64_t seed, int64_t row_offset,
+                float* d_X, void* stream) {
+  rnvp_desc* d = const_cast<rnvp_desc*>(dc);
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (N < 0 || row_offset < 0 || !d_packed || (N > 0 && !d_X)) return fail(RNVP_EINVAL, "rnvp_sample: bad argument");
+  if ((d->Cd > 0) != (d_C != nullptr) && N > 0) return fail(RNVP_EINVAL, "rnvp_sample: C must be given iff cond_size > 0");
+  if (use_mma(d))
+    return run_mma(d, 1, 0, d->L, d_packed, nullptr, d_C, nullptr, N, d_X, nullptr, nullptr, (cudaStream_t)stream, nullptr,
+                   nullptr, nullptr, 0.f, seed, row_offset);
+  if (d->small_ok)
+    return run_small(d, 1, 0, d->L, d_packed, nullptr, d_C, nullptr, N, d_X, nullptr, nullptr, (cudaStream_t)stream,
+                     nullptr, nullptr, 0.f, seed, row_offset);
+  RnvpKArgs a;
+  memset(&a, 0, sizeof(a));
+  a.packed = d_packed; a.X = nullptr; a.C = d_C; a.N = N; a.out_x = d_X; a.seed = seed; a.row_offset = row_offset;
+  return run_tile(d, 1, 0, d->L, a, nullptr, 0, (cudaStream_t)stream);
 }
 
 int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, const float* d_C,

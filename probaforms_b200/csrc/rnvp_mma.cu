@@ -31,6 +31,7 @@
 #include <stdint.h>
 #include "tc05.cuh"
 #include "rnvp_mma.h"
+#include "rnvp_philox.cuh"
 
 namespace {
 using namespace tc05;
@@ -420,7 +421,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
       float xa[DH], xb[DH], cc[CDMAX], ld = 0.0f;       // even features, odd features, condition
 #pragma unroll
       for (int m = 0; m < DH / 2; ++m) {
-        float4 v = valid ? __ldg(reinterpret_cast<const float4*>(a.X + src * D) + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 1 && a.X == nullptr) { if (valid) v = rnvp_rng::normal4(a.seed, a.row_offset + row, m); }   // sampling: in-kernel prior draw
+        else if (valid) v = __ldg(reinterpret_cast<const float4*>(a.X + src * D) + m);
         xa[2 * m] = v.x; xb[2 * m] = v.y; xa[2 * m + 1] = v.z; xb[2 * m + 1] = v.w;
       }
 #pragma unroll

@@ -28,4 +28,7 @@ struct RnvpMmaArgs {
   long long Npad;
   long long* trace;            // development aid (rnvp_debug_set_trace): CTA 0 logs (tag, clock64) pairs of the backward sweep
   int wt_floats;               // floats of one transposed image (W2T, then W1T) per layer; 0 unless do_bwd
+  // MODE 1 with X == nullptr: latent rows drawn in-kernel (rnvp_philox.cuh), keyed on row_offset + row
+  unsigned long long seed;
+  long long row_offset;
 };

@@ -99,5 +99,8 @@ struct RnvpKArgs {
   int gstash_row, gstash_half;        // floats per row (L*2*half) and per half (|T|max)
   float scale;                        // backward: d(out)/d(logp_row); g_logdet = scale, g_z = -z*scale
   int D, Cd;
+  // inverse program with X == nullptr: latent rows drawn in-kernel (rnvp_philox.cuh), keyed on row_offset + row
+  unsigned long long seed;
+  long long row_offset;
   RnvpSmem sm;
 };

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "rnvp_small.h"
+#include "rnvp_philox.cuh"
 
 namespace {
 
@@ -106,10 +107,26 @@ __global__ void __launch_bounds__(THREADS) rnvp_small_kernel(const RnvpSmallArgs
       const bool ok = row[r] < a.N;
       const long long src = ok ? (a.idx ? a.idx[row[r]] : row[r]) : 0;
       ld[r] = 0.0f;
+      if (MODE == 1 && a.X == nullptr) {      // sampling: prior draws generated here, keyed on the global row index
 #pragma unroll
-      for (int e = 0; e < NE; ++e) {
-        xe[r][e] = (ok && 2 * e < D) ? __ldg(a.X + src * D + 2 * e) : 0.0f;
-        xo[r][e] = (ok && 2 * e + 1 < D) ? __ldg(a.X + src * D + 2 * e + 1) : 0.0f;
+        for (int q = 0; q < (2 * NE + 3) / 4; ++q) {
+          const float4 v = rnvp_rng::normal4(a.seed, a.row_offset + row[r], q);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int j = 4 * q + m;
+            if (j < 2 * NE) {
+              if (j & 1) xo[r][j >> 1] = (ok && j < D) ? vv[m] : 0.0f;
+              else xe[r][j >> 1] = (ok && j < D) ? vv[m] : 0.0f;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          xe[r][e] = (ok && 2 * e < D) ? __ldg(a.X + src * D + 2 * e) : 0.0f;
+          xo[r][e] = (ok && 2 * e + 1 < D) ? __ldg(a.X + src * D + 2 * e + 1) : 0.0f;
+        }
       }
 #pragma unroll
       for (int k = 0; k < (NC > 0 ? NC : 1); ++k) c[r][k] = (NC > 0 && ok && k < Cd) ? __ldg(a.C + src * Cd + k) : 0.0f;

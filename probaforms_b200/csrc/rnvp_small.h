@@ -19,4 +19,7 @@ struct RnvpSmallArgs {
   const int* s2g;
   float* loss_sum;
   float scale;
+  // inverse mode with X == nullptr: the latent rows are drawn in-kernel (rnvp_philox.cuh), keyed on row_offset + row
+  unsigned long long seed;
+  long long row_offset;
 };

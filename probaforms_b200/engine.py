@@ -192,6 +192,20 @@ class FlowEngine:
             self.launches += 1
         return Xo
 
+    def sample(self, n, Cn=None, seed=0, row_offset=0, out=None):
+        """NormalizingFlow.sample in one launch: prior draws generated in-kernel (Philox keyed on the global row index
+        ``row_offset + r``), then all layers in reverse (nflow.py:141-143).  ``Cn`` may be a tensor of n rows or None."""
+        n = int(n)
+        Cn = self._check_cond(Cn, n)
+        Xo = out if out is not None else torch.empty(n, self.D, dtype=torch.float32, device=self.device)
+        if n > 0:
+            with self._guard():
+                _lib.check(self.lib.rnvp_sample(self._desc, _ptr(self.packed), _ptr(Cn), n,
+                                                C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), int(row_offset), _ptr(Xo),
+                                                self._stream()), "rnvp_sample")
+            self.launches += 1
+        return Xo
+
     def zero_grads(self):
         self._gbuf.zero_()
         self.launches += 1

@@ -1,0 +1,214 @@
+"""Host <-> device row traffic of ``RealNVP.fit`` / ``.sample``.
+
+The reference copies the whole numpy data set through ``torch.tensor(X, dtype=torch.float32)``
+(realnvp.py:226-228) and returns samples through ``.cpu().detach().numpy()`` (realnvp.py:281).  Once a
+fit step takes a millisecond those two copies are the wall-clock bound, so here
+
+* ``upload_resident`` converts (float64 -> float32) and uploads in chunks through two pinned staging
+  buffers: the host conversion of chunk k+1 overlaps the H2D copy of chunk k;
+* ``StepStreamer`` feeds the fit loop with exactly the rows each step needs -- THIS rank's slice of the
+  epoch permutation, gathered and converted by ``rnvp_host_gather_rows`` into a ring of pinned buffers on
+  a helper thread and uploaded on a copy stream one or two steps ahead of the kernels.  Under data
+  parallelism every rank therefore uploads 1/world of the rows instead of the whole set;
+* ``rows_to_numpy`` brings results back through pinned buffers with a multi-threaded copy into the
+  fresh numpy array the API contract returns (first-touch page faults are spread over several cores).
+
+torch is plumbing here (pinned memory, streams, events); the byte moving is the C ABI's
+``rnvp_host_*`` entry points (include/rnvp.h).
+"""
+import ctypes as C
+import os
+import queue
+import threading
+
+import numpy as np
+import torch
+
+
+def host_threads():
+    """Host threads one process may use for gathers / copies: the box's cores shared by the local ranks."""
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    return max(1, min(8, (os.cpu_count() or 1) // max(local_world, 1)))
+
+
+def host_rows(A):
+    """numpy / CPU-torch rows -> C-contiguous 2-D numpy array of float32 or float64 (no copy if it already is one)."""
+    if isinstance(A, torch.Tensor):
+        A = A.detach().numpy() if A.device.type == "cpu" else None
+        if A is None:
+            raise TypeError("host_rows: expected host data")
+    A = np.asarray(A)
+    if A.dtype not in (np.float32, np.float64):
+        A = A.astype(np.float32)
+    if A.ndim != 2:
+        raise ValueError(f"rows must be 2-D [n, width], got shape {A.shape}")
+    return np.ascontiguousarray(A)
+
+
+def gather_into(lib, arr, idx, row0, n, dst, threads=None):
+    """dst[:n] = float32(arr[idx[:n]]) (idx: contiguous int64 numpy array / torch tensor, or None for rows row0..)."""
+    if n <= 0:
+        return
+    iptr = None
+    if idx is not None:
+        iptr = C.c_void_p(idx.data_ptr() if isinstance(idx, torch.Tensor) else idx.ctypes.data)
+    rc = lib.rnvp_host_gather_rows(C.c_void_p(arr.ctypes.data), 1 if arr.dtype == np.float64 else 0, arr.shape[1], iptr,
+                                   int(row0), int(n), C.c_void_p(dst.data_ptr()), threads or host_threads())
+    if rc != 0:
+        raise RuntimeError(f"rnvp_host_gather_rows failed (code {rc})")
+
+
+def _pinned(shape, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+
+
+def upload_resident(lib, A, dev, chunk_bytes=32 << 20):
+    """Whole row set -> contiguous float32 device tensor [n, w].  Pinned float32 torch tensors go up in one asynchronous
+    copy; everything else (numpy float64 / float32, pageable tensors) is converted chunk by chunk into two pinned
+    staging buffers so that the host pass over chunk k+1 runs while chunk k is on the bus."""
+    if isinstance(A, torch.Tensor):
+        if A.device.type != "cpu":
+            return A.to(device=dev, dtype=torch.float32).contiguous()
+        if A.dtype == torch.float32 and A.is_pinned() and A.is_contiguous() and A.dim() == 2:
+            return A.to(dev, non_blocking=True)
+    arr = host_rows(A)
+    n, w = arr.shape
+    out = torch.empty(n, w, dtype=torch.float32, device=dev)
+    if n == 0:
+        return out
+    rows = max(1, min(n, chunk_bytes // (4 * w)))
+    if n * w * 4 <= (1 << 20):                      # small sets: one synchronous hop is cheapest
+        stage = torch.empty(n, w, dtype=torch.float32)
+        gather_into(lib, arr, None, 0, n, stage, threads=1)
+        out.copy_(stage)
+        return out
+    stage = [_pinned((rows, w)), _pinned((rows, w))]
+    done = [None, None]
+    copy_stream = torch.cuda.Stream(device=dev)
+    for k, r0 in enumerate(range(0, n, rows)):
+        m = min(rows, n - r0)
+        s = k & 1
+        if done[s] is not None:
+            done[s].synchronize()
+        gather_into(lib, arr, None, r0, m, stage[s])
+        with torch.cuda.stream(copy_stream):
+            out[r0:r0 + m].copy_(stage[s][:m], non_blocking=True)
+            done[s] = torch.cuda.Event()
+            done[s].record(copy_stream)
+    torch.cuda.current_stream(dev).wait_stream(copy_stream)
+    for e in done:
+        if e is not None:
+            e.synchronize()                         # the staging buffers die with this call
+    return out
+
+
+def rows_to_numpy(lib, t, chunk_bytes=32 << 20):
+    """CUDA tensor -> fresh numpy array (the return contract of RealNVP.sample, realnvp.py:281): D2H in chunks through
+    two pinned buffers, each chunk copied into the result by several host threads while the next one is on the bus."""
+    t = t.detach()
+    if t.device.type != "cuda" or t.numel() * t.element_size() <= (1 << 20) or t.dtype != torch.float32:
+        return t.cpu().numpy()
+    t = t.contiguous()
+    out = np.empty(tuple(t.shape), dtype=np.float32)
+    flat = t.view(-1)
+    n = flat.numel()
+    per = max(1, chunk_bytes // 4)
+    stage = [_pinned((min(per, n),)), _pinned((min(per, n),))]
+    evs = [None, None]
+    dev = t.device
+    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream.wait_stream(torch.cuda.current_stream(dev))
+    chunks = [(o, min(per, n - o)) for o in range(0, n, per)]
+    threads = host_threads()
+
+    def launch(k):
+        o, m = chunks[k]
+        with torch.cuda.stream(copy_stream):
+            stage[k & 1][:m].copy_(flat[o:o + m], non_blocking=True)
+            evs[k & 1] = torch.cuda.Event()
+            evs[k & 1].record(copy_stream)
+
+    launch(0)
+    base = out.ctypes.data
+    for k, (o, m) in enumerate(chunks):
+        evs[k & 1].synchronize()
+        if k + 1 < len(chunks):
+            launch(k + 1)
+        lib.rnvp_host_copy(C.c_void_p(base + 4 * o), C.c_void_p(stage[k & 1].data_ptr()), 4 * m, threads)
+    return out
+
+
+class StepStreamer:
+    """Rows of every optimisation step of one ``fit`` call, streamed: a helper thread gathers (and converts) this rank's
+    slice of each batch into a ring of pinned buffers and enqueues the H2D copies on its own stream; ``next()`` hands the
+    fit loop device tensors ``(X_dev, C_dev, m)`` once the compute stream has been made to wait for their copy.
+
+    ``plan`` is an iterable of ``(get_idx, lo, hi)``: ``get_idx(hi)`` returns a host int64 array whose entries [lo, hi)
+    are final (it may block: the epoch permutation is itself produced incrementally)."""
+
+    SLOTS = 3
+
+    def __init__(self, lib, X, Cn, dev, max_rows, plan):
+        self.lib, self.dev = lib, dev
+        self.X, self.Cn = host_rows(X), (host_rows(Cn) if Cn is not None else None)
+        w, wc = self.X.shape[1], (self.Cn.shape[1] if self.Cn is not None else 0)
+        self.hx = [_pinned((max_rows, w)) for _ in range(self.SLOTS)]
+        self.hc = [_pinned((max_rows, wc)) for _ in range(self.SLOTS)] if wc else None
+        self.dx = [torch.empty(max_rows, w, dtype=torch.float32, device=dev) for _ in range(self.SLOTS)]
+        self.dc = [torch.empty(max_rows, wc, dtype=torch.float32, device=dev) for _ in range(self.SLOTS)] if wc else None
+        self.free = [None] * self.SLOTS            # event: the step that used the slot has finished
+        self.q = queue.Queue(maxsize=self.SLOTS - 1)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.bytes_h2d = 0
+        self._err = None
+        self._plan = plan
+        self._thread = threading.Thread(target=self._work, daemon=True)
+        self._thread.start()
+
+    def _work(self):
+        try:
+            torch.cuda.set_device(self.dev)
+            threads = host_threads()
+            for k, (get_idx, lo, hi) in enumerate(self._plan):
+                s = k % self.SLOTS
+                m = hi - lo
+                ev = self.free[s]
+                if ev is not None:
+                    ev.synchronize()                # kernels of the step that last used this slot are done
+                idx = get_idx(hi)
+                sl = idx[lo:hi]
+                gather_into(self.lib, self.X, sl, 0, m, self.hx[s], threads)
+                if self.hc is not None:
+                    gather_into(self.lib, self.Cn, sl, 0, m, self.hc[s], threads)
+                with torch.cuda.stream(self.copy_stream):
+                    self.dx[s][:m].copy_(self.hx[s][:m], non_blocking=True)
+                    if self.hc is not None:
+                        self.dc[s][:m].copy_(self.hc[s][:m], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(self.copy_stream)
+                self.bytes_h2d += 4 * m * (self.X.shape[1] + (self.Cn.shape[1] if self.Cn is not None else 0))
+                self.q.put((s, m, done))
+            self.q.put(None)
+        except BaseException as e:                  # surfaced by next()
+            self._err = e
+            self.q.put(None)
+
+    def next(self):
+        """(X_dev, C_dev, rows, slot) of the next step; the current stream waits for its upload."""
+        item = self.q.get()
+        if item is None:
+            if self._err is not None:
+                raise self._err
+            raise StopIteration
+        s, m, done = item
+        torch.cuda.current_stream(self.dev).wait_event(done)
+        return self.dx[s], (self.dc[s] if self.dc is not None else None), m, s
+
+    def release(self, slot):
+        """Call after the step's kernels were enqueued: the slot is recycled once they have run."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.free[slot] = ev
+
+    def close(self):
+        self._thread.join()

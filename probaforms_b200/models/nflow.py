@@ -81,6 +81,7 @@ class NormalizingFlow(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_engine"] = None
+        state.pop("_replicas", None)
         return state
 
     def __setstate__(self, state):
@@ -164,33 +165,55 @@ class NormalizingFlow(nn.Module):
         eng, eps, C = self._prep(eps, C)
         return eng.inverse(eps, C)
 
-    def sample(self, C):
-        """nflow.py:120-145: ``C`` is a [n, cond_size] tensor or a Python int (unconditional)."""
+    def _replica(self, dev):
+        """Engine holding a copy of this flow's weights on another CUDA device (multi-GPU sample / log-prob of one
+        process: rows shard with no communication).  Refreshed from the primary at every call."""
+        eng = self._fused(repack=False)
+        dev = torch.device(dev)
+        if dev == eng.device:
+            return self._fused()
+        reps = self.__dict__.setdefault("_replicas", {})
+        rep = reps.get(dev)
+        if rep is None:
+            rep = FlowEngine(eng.D, eng.Cd, eng.L, eng.hidden, eng.activation, dev)
+            reps[dev] = rep
+        rep.flat.copy_(eng.flat)
+        with torch.cuda.device(dev):
+            rep.pack()
+        return rep
+
+    def sample(self, C, seed=None, row_offset=0, out=None):
+        """nflow.py:120-145: ``C`` is a [n, cond_size] tensor or a Python int (unconditional).
+
+        The prior draw (nflow.py:141) is generated inside the inverse kernel: latent element (r, j) is a function of
+        (seed, row_offset + r, j) only, so row blocks produced on different GPUs or in different launches are the rows
+        of one big request.  ``seed=None`` draws one int64 from torch's global CPU generator (reproducible under
+        ``torch.manual_seed`` like upstream's ``prior.sample``).  ``sample_from_noise`` is the parity mode."""
         if type(C) == type(1):           # numpy ints deliberately do not qualify, as upstream (nflow.py:135)
             n, C = C, None
         else:
             n = len(C)
         eng = self._fused()
-        # prior.sample((n,)) of MultivariateNormal(0, I) == randn(n, D) on the prior's device generator
-        eps = torch.randn(n, eng.D, dtype=torch.float32, device=eng.device)
+        if seed is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
         if C is not None:
             C = torch.as_tensor(C, dtype=torch.float32, device=eng.device)
-        return eng.inverse(eps, C)
+        return eng.sample(n, C, seed=seed, row_offset=row_offset, out=out)
 
-    def sample_many(self, C, n_draws):
+    def sample_many(self, C, n_draws, seed=None):
         """``n_draws`` independent ``sample(C)`` results as one [n_draws, n, D] tensor: the conditions are uploaded and
         validated once, every draw is one launch into its slice of the output (the notebooks' Monte-Carlo pattern
-        ``for i in range(1000): model.sample(C)``, docs/examples/regression.ipynb cell 13).  Draw k consumes the device
+        ``for i in range(1000): model.sample(C)``, docs/examples/regression.ipynb cell 13).  Draw k consumes the global
         generator exactly like the k-th call of ``sample`` would."""
         if type(C) == type(1):
             n, C = C, None
         else:
             n = len(C)
-        eng = self._fused(repack=False)
+        eng = self._fused()               # repack: in-place parameter edits (load_state_dict, external optimisers) count
         if C is not None:
             C = torch.as_tensor(C, dtype=torch.float32, device=eng.device)
         out = torch.empty(int(n_draws), n, eng.D, dtype=torch.float32, device=eng.device)
         for k in range(int(n_draws)):
-            eps = torch.randn(n, eng.D, dtype=torch.float32, device=eng.device)
-            eng.inverse(eps, C, out=out[k])
+            sd = int(torch.empty((), dtype=torch.int64).random_().item()) if seed is None else int(seed) + k
+            eng.sample(n, C, seed=sd, out=out[k])
         return out

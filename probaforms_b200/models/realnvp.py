@@ -139,12 +139,60 @@ class FusedAdam(torch.optim.Adam):
         super().__init__(flow.parameters(), lr=lr, weight_decay=weight_decay)
         self._flow = weakref.ref(flow)
 
+    # torch.optim.Optimizer pickles only defaults / state / param_groups: the weak reference to the flow is dropped
+    # and re-linked by the owner (RealNVP.__setstate__ / _relink) or lazily from the parameters' flow
+    def __getstate__(self):
+        state = super().__getstate__()
+        state.pop("_flow", None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        if "_flow" not in self.__dict__:
+            self._flow = lambda: None
+
+    def _relink(self, flow):
+        self._flow = weakref.ref(flow)
+
+    def _live_flow(self):
+        flow = self._flow() if getattr(self, "_flow", None) is not None else None
+        if flow is None:
+            raise RuntimeError("FusedAdam lost its flow (copied / unpickled on its own?): call opt._relink(nf) or use "
+                               "the RealNVP object, which re-links it")
+        return flow
+
     def _publish_state(self, eng):
-        for p, (off, numel) in zip(self._flow()._ordered_params(), eng.tensor_spans):
+        for p, (off, numel) in zip(self._live_flow()._ordered_params(), eng.tensor_spans):
             st = self.state[p]
             st["step"] = torch.tensor(float(eng.adam_steps))
             st["exp_avg"] = eng.exp_avg[off:off + numel].view(p.shape)
             st["exp_avg_sq"] = eng.exp_avg_sq[off:off + numel].view(p.shape)
+
+    def _import_state(self, eng):
+        """Copy ``state[p]`` (e.g. from ``load_state_dict`` of a checkpoint, or carried over an engine rebuild) into the
+        engine's flat moment buffers and step counter, so that resuming continues the reference's Adam trajectory."""
+        params = self._live_flow()._ordered_params()
+        if not any(p in self.state and "exp_avg" in self.state[p] for p in params):
+            return
+        eng._ensure_adam_state()
+        steps = 0
+        for p, (off, numel) in zip(params, eng.tensor_spans):
+            st = self.state.get(p)
+            if not st or "exp_avg" not in st:
+                continue
+            m, v = st["exp_avg"], st["exp_avg_sq"]
+            if m.data_ptr() != eng.exp_avg.data_ptr() + 4 * off:
+                eng.exp_avg[off:off + numel].copy_(m.reshape(-1))
+                eng.exp_avg_sq[off:off + numel].copy_(v.reshape(-1))
+            steps = max(steps, int(float(st.get("step", 0))))
+        eng.adam_steps = steps
+        self._publish_state(eng)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        flow = self._flow() if getattr(self, "_flow", None) is not None else None
+        if flow is not None and flow._engine is not None:
+            self._import_state(flow._fused(repack=False))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -152,8 +200,11 @@ class FusedAdam(torch.optim.Adam):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        flow = self._flow()
+        flow = self._live_flow()
         eng = flow._fused(repack=False)
+        if getattr(eng, "_adam_owner", None) is not self:       # new engine (device move, unpickle): carry the moments over
+            self._import_state(eng)
+            eng._adam_owner = self
         group = self.param_groups[0]
         gflat = torch.zeros(eng.P, dtype=torch.float32, device=eng.device)
         for p, (off, numel) in zip(flow._ordered_params(), eng.tensor_spans):
@@ -173,10 +224,13 @@ class RealNVP(GenModel):
     """
 
     def __init__(self, n_layers=8, hidden=(10,), activation='tanh',
-                 batch_size=32, n_epochs=10, lr=0.0001, weight_decay=0, verbose=0, shuffle='reference'):
+                 batch_size=32, n_epochs=10, lr=0.0001, weight_decay=0, verbose=0, shuffle='reference', ingest='auto'):
         super().__init__()
         if shuffle not in ('reference', 'device'):
             raise ValueError("shuffle must be 'reference' or 'device'")
+        if ingest not in ('auto', 'resident', 'stream'):
+            raise ValueError("ingest must be 'auto', 'resident' or 'stream'")
+        self.ingest = ingest                       # additive, see fit()
         # 'reference' (default): every epoch's batches have exactly the reference's composition (realnvp.py:237).
         # 'device' (additive, opt-in): the epoch order is a torch.randperm on the GPU, seeded from the same per-epoch
         # seed -- statistically the same training, not the same batches; it removes the sequential CPU shuffle
@@ -221,19 +275,40 @@ class RealNVP(GenModel):
             self.nf._fused()
             self.opt = FusedAdam(self.nf, lr=self.lr, weight_decay=self.weight_decay)
 
-    @staticmethod
-    def _to_device(A, dev):
-        """numpy/torch -> contiguous float32 rows on the device (realnvp.py:226-228)."""
-        if isinstance(A, torch.Tensor):
-            # pinned host tensors upload asynchronously (the epoch's row order is computed meanwhile)
-            nb = A.device.type == "cpu" and A.is_pinned()
-            return A.to(device=dev, dtype=torch.float32, non_blocking=nb).contiguous()
-        A = np.asarray(A)
-        if A.dtype != np.float32:
-            A = A.astype(np.float32)
-        if A.ndim > 0:                                   # (ascontiguousarray would promote a 0-d value to 1-d)
-            A = np.ascontiguousarray(A)
-        return torch.from_numpy(A).to(dev)
+    def __setstate__(self, state):
+        super().__setstate__(state) if hasattr(super(), "__setstate__") else self.__dict__.update(state)
+        if getattr(self, "opt", None) is not None and getattr(self, "nf", None) is not None:
+            self.opt._relink(self.nf)               # pickle / deepcopy drop the optimiser's weak reference to the flow
+
+    def _to_device(self, A, dev):
+        """numpy/torch -> contiguous float32 rows on the device (realnvp.py:226-228), chunked through pinned staging
+        buffers with the float64 -> float32 conversion fused into the host pass (probaforms_b200/ingest.py)."""
+        if isinstance(A, torch.Tensor) and (A.device.type != "cpu" or A.dim() != 2):
+            return A.to(device=dev, dtype=torch.float32).contiguous()
+        if not isinstance(A, torch.Tensor) and np.asarray(A).ndim != 2:
+            return torch.as_tensor(np.asarray(A), dtype=torch.float32).to(dev)     # let the shape checks speak
+        from ..ingest import upload_resident
+        return upload_resident(self.nf._fused(repack=False).lib, A, dev)
+
+    def _check_fit_inputs(self, X, C, eng):
+        """What the reference's TensorDataset / first Linear would reject (realnvp.py:229-231): row-count mismatch,
+        non-2-D arrays, and -- on a warm start -- widths that differ from the flow that was built."""
+        xs = tuple(X.shape)
+        if len(xs) != 2:
+            raise ValueError(f"X must be 2-D [n, var_size], got shape {xs}")
+        if xs[1] != eng.D:
+            raise ValueError(f"X has {xs[1]} columns but the fitted flow has var_size={eng.D}")
+        if C is None:
+            if eng.Cd != 0:
+                raise ValueError(f"this flow was built with cond_size={eng.Cd}: C is required")
+            return
+        cs = tuple(C.shape)
+        if len(cs) != 2:
+            raise ValueError(f"C must be 2-D [n, cond_size], got shape {cs}")
+        if cs[0] != xs[0]:
+            raise ValueError(f"Size mismatch between tensors: X has {xs[0]} rows, C has {cs[0]}")
+        if cs[1] != eng.Cd:
+            raise ValueError(f"C has {cs[1]} columns but the fitted flow has cond_size={eng.Cd}")
 
     # ------------------------------------------------------------------ fit
     def fit(self, X, C=None):
@@ -247,7 +322,17 @@ class RealNVP(GenModel):
         global batch of ``batch_size`` rows is split into contiguous per-rank slices and the packed
         gradient (+loss) buffer is all-reduced once per step (NCCL), which reproduces the
         single-process trajectory up to fp32 summation order.
+
+        Ingestion (``ingest=`` constructor option): ``'resident'`` uploads the whole set once (chunked, conversion
+        fused) and gathers batches on the device; ``'stream'`` uploads, one step ahead of the kernels, only the rows
+        THIS rank needs for each step (host gather + conversion into pinned buffers on a helper thread);
+        ``'auto'`` streams when that moves fewer bytes (host data, n_epochs <= world size, large batches).
         """
+        if not hasattr(X, "shape") or (C is not None and not hasattr(C, "shape")):
+            X = np.asarray(X)
+            C = None if C is None else np.asarray(C)
+        if len(tuple(X.shape)) != 2:
+            raise ValueError(f"X must be 2-D [n, var_size], got shape {tuple(X.shape)}")
         self._model_init(X, C)
         dev = self._device
         dist = torch.distributed
@@ -255,14 +340,29 @@ class RealNVP(GenModel):
         rank = dist.get_rank() if world > 1 else 0
         n = X.shape[0]
         bs = int(self.batch_size)
+        eng = self.nf._fused()
+        self._check_fit_inputs(X, C, eng)
+        if getattr(eng, "_adam_owner", None) is not self.opt:       # rebuilt engine / loaded checkpoint: resume Adam
+            self.opt._import_state(eng)
+            eng._adam_owner = self.opt
+        device_shuffle = getattr(self, "shuffle", "reference") == "device"
+        on_host = not (isinstance(X, torch.Tensor) and X.device.type != "cpu")
+        mode = getattr(self, "ingest", "auto")
+        stream_rows = mode == "stream" or (mode == "auto" and on_host and self.n_epochs <= world
+                                           and min(bs, n) // world >= 8192)
+        stream_rows = stream_rows and on_host and n > 0
         # identical row order on every rank (the sampler seed of rank 0 is broadcast); computed one epoch ahead on a
         # helper thread, the first one while the rows are uploaded
-        eng = self.nf._fused()
-        device_shuffle = getattr(self, "shuffle", "reference") == "device"
         perms = None if device_shuffle else PermutationPrefetcher(
             n, self.n_epochs, device=dev if world > 1 else None, lib=eng.lib, host_buffers=self._perm_host)
+        streamed_perm = perms is not None and perms.streaming
+        bounds = batch_bounds(n, bs)
+        if stream_rows:
+            return self._fit_streamed(X, C, eng, perms, bounds, rank, world, device_shuffle)
         Xd = self._to_device(X, dev)
         Cd = self._to_device(C, dev) if C is not None else None
+        Xd = eng._check_rows(Xd, eng.D, "X")
+        Cd = eng._check_cond(Cd, n)
         perm_dev = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
 
         epochs = range(self.n_epochs)
@@ -275,7 +375,6 @@ class RealNVP(GenModel):
         for _ in epochs:
             # the epoch's row order streams in from a helper thread (rnvp_perm_*, same order as the reference's
             # DataLoader): a step only waits for its own batch, the tail of the shuffle overlaps the GPU work
-            bounds = batch_bounds(n, bs)
             losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
             loss_ptr = losses.data_ptr()
             if device_shuffle:
@@ -283,8 +382,11 @@ class RealNVP(GenModel):
                 gen.manual_seed(epoch_seed(device=dev if world > 1 else None) & 0x7FFFFFFFFFFFFFFF)
                 perm_dev = torch.randperm(n, device=dev, generator=gen)
                 stream, copied = None, n
-            else:
+            elif streamed_perm:
                 stream, copied = perms.next_stream(), 0
+            else:                                           # very large n: torch.randperm's 64-bit scheme, whole tensor
+                perm_dev.copy_(perms.next(), non_blocking=True)
+                stream, copied = None, n
             perm_ptr = perm_dev.data_ptr()
             for s, (b0, nb) in enumerate(bounds):           # last partial batch is kept (drop_last=False)
                 if copied < b0 + nb:                        # upload whatever is final by now, at least this batch
@@ -302,17 +404,170 @@ class RealNVP(GenModel):
                 bar.set_description(f"loss: {float(host[-1]):.4f}")
         self.opt._publish_state(eng)
 
+    def _fit_streamed(self, X, C, eng, perms, bounds, rank, world, device_shuffle):
+        """The fit loop with the rows of every step streamed from the host (see ``fit`` and ingest.StepStreamer): the
+        batches are the same slices of the same epoch permutations as in resident mode, so the trajectory is identical."""
+        from ..ingest import StepStreamer
+        dev, n = self._device, X.shape[0]
+        epoch_orders = []                                   # one provider per epoch: get(hi) -> host int64 array
+
+        def order_provider():
+            if device_shuffle:
+                gen = torch.Generator(device=dev)
+                gen.manual_seed(epoch_seed(device=dev if world > 1 else None) & 0x7FFFFFFFFFFFFFFF)
+                host = torch.randperm(n, device=dev, generator=gen).cpu().numpy()
+                return lambda hi: host
+            if perms.streaming:
+                sp = perms.next_stream()
+                return lambda hi: sp.wait(hi).numpy()
+            host = perms.next().numpy()
+            return lambda hi: host
+
+        # seeds are drawn on this thread, in epoch order, exactly as in resident mode; epoch e+1's order is requested when
+        # epoch e starts so that at most two epoch orders are in flight (the prefetcher alternates two host buffers)
+        import threading
+        ready = [threading.Event() for _ in range(self.n_epochs)]
+        epoch_orders = [None] * self.n_epochs
+
+        def plan():
+            for e in range(self.n_epochs):
+                ready[e].wait()
+                get = epoch_orders[e]
+                for (b0, nb) in bounds:
+                    lo, hi = shard_bounds(b0, nb, rank, world)
+                    yield get, lo, hi
+
+        max_rows = max(shard_bounds(b0, nb, rank, world)[1] - shard_bounds(b0, nb, rank, world)[0] for b0, nb in bounds)
+        epoch_orders[0] = order_provider()
+        ready[0].set()
+        streamer = StepStreamer(eng.lib, X, C, dev, max(max_rows, 1), plan())
+        eng.zero_grads()
+        try:
+            for e in range(self.n_epochs):
+                if e + 1 < self.n_epochs:
+                    epoch_orders[e + 1] = order_provider()
+                    ready[e + 1].set()
+                losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
+                loss_ptr = losses.data_ptr()
+                for s, (b0, nb) in enumerate(bounds):
+                    Xs, Cs, m, slot = streamer.next()
+                    eng.fit_step(Xs, Cs, None, m, nb, self.lr, self.weight_decay, loss_ptr + 4 * s, world=world)
+                    streamer.release(slot)
+                host = losses.cpu()
+                self.loss_history.extend(host.unbind(0))
+        finally:
+            for ev in ready:
+                ev.set()
+        streamer.close()
+        self.h2d_bytes_last_fit = streamer.bytes_h2d
+        self.opt._publish_state(eng)
+
     # ------------------------------------------------------------------ sample
-    def sample(self, C=100, n_draws=None):
+    def _shard_of(self, n):
+        """This rank's contiguous block [lo, hi) of an n-row request under an initialised process group."""
+        dist = torch.distributed
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        return (n * rank) // world, (n * (rank + 1)) // world, world
+
+    def sample(self, C=100, n_draws=None, seed=None, devices=None, shard=False):
         """Draw rows for the given conditions [n, cond_size], or ``C`` rows if it is a Python int
         (realnvp.py:265-282).  Returns a float32 numpy array [n, var_size].
 
-        ``n_draws=k`` (additive, not upstream) returns [k, n, var_size]: k independent draws for the same conditions
-        with one upload of ``C`` and one download of the result -- the notebooks' ``for i in range(1000):
-        model.sample(C)`` loop as a single call."""
-        if type(C) != type(1):
-            C = self._to_device(C, self._device)
-        if n_draws is not None:
-            return self.nf.sample_many(C, n_draws).cpu().detach().numpy()
-        X = self.nf.sample(C).cpu().detach().numpy()
-        return X
+        The prior draw happens inside the inverse kernel (Philox keyed on the row index): one launch, no noise tensor.
+        ``seed`` (additive) fixes it; by default one int64 is drawn from torch's global CPU generator per call, so
+        ``torch.manual_seed`` makes ``sample`` reproducible, as upstream.
+
+        Additive, not upstream:
+        ``n_draws=k`` returns [k, n, var_size]: k independent draws for the same conditions with one upload of ``C`` and
+        one download of the result -- the notebooks' ``for i in range(1000): model.sample(C)`` loop as a single call.
+        ``devices=[0, 1, ...]`` splits the rows into contiguous blocks over several GPUs of this process (weights are
+        replicated, no communication); ``shard=True`` under an initialised ``torch.distributed`` group makes every
+        rank return only its block ``[n*rank//world, n*(rank+1)//world)`` of the request.  Because the noise of row r
+        depends only on (seed, r), both give exactly the rows a single GPU would."""
+        from ..ingest import rows_to_numpy
+        if self.nf is None:
+            raise RuntimeError("RealNVP.sample: call fit() first")
+        eng = self.nf._fused()
+        is_int = type(C) == type(1)
+        n = C if is_int else len(C)
+        if seed is None:
+            seeds = [int(torch.empty((), dtype=torch.int64).random_().item()) for _ in range(n_draws or 1)]
+        else:
+            seeds = [int(seed) + k for k in range(n_draws or 1)]
+        if shard:
+            lo, hi, world = self._shard_of(n)
+            if world > 1:                                     # every rank must use rank 0's seeds
+                t = torch.tensor(seeds, dtype=torch.int64, device=self._device)
+                torch.distributed.broadcast(t, src=0)
+                seeds = [int(v) for v in t.cpu()]
+        else:
+            lo, hi = 0, n
+        if devices is not None and len(devices) > 0:
+            out = self._sample_multi_device(C, is_int, lo, hi, seeds, list(devices))
+        else:
+            Cd = None
+            if not is_int:
+                Cs = C[lo:hi]
+                Cd = self._to_device(Cs, self._device)
+            outs = [eng.sample(hi - lo, Cd, seed=sd, row_offset=lo) for sd in seeds]
+            out = torch.stack(outs) if n_draws is not None else outs[0]
+            return rows_to_numpy(eng.lib, out)
+        return out if n_draws is not None else out[0]
+
+    def _sample_multi_device(self, C, is_int, lo, hi, seeds, devices):
+        """Row blocks of [lo, hi) on several GPUs of this process: replicas of the weights, one launch per (device, draw),
+        results copied back into one host array."""
+        n = hi - lo
+        D = self.nf._fused(repack=False).D
+        out = np.empty((len(seeds), n, D), dtype=np.float32)
+        pending = []
+        for k, d in enumerate(devices):
+            b0, b1 = lo + (n * k) // len(devices), lo + (n * (k + 1)) // len(devices)
+            if b1 <= b0:
+                continue
+            dev = torch.device("cuda", d) if not isinstance(d, torch.device) else d
+            eng = self.nf._replica(dev)
+            with torch.cuda.device(dev):
+                Cd = None if is_int else self._to_device(C[b0:b1], dev)
+                res = torch.stack([eng.sample(b1 - b0, Cd, seed=sd, row_offset=b0) for sd in seeds])
+                host = torch.empty(res.shape, dtype=torch.float32, pin_memory=True)
+                host.copy_(res, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            pending.append((b0 - lo, b1 - lo, host, ev, res))
+        for a, b, host, ev, _ in pending:
+            ev.synchronize()
+            out[:, a:b] = host.numpy()
+        return out
+
+    def log_prob_rows(self, X, C=None, devices=None, shard=False):
+        """Per-row log-density as a float32 numpy array [n] (additive; nflow.py:107-115 without the mean).  ``devices`` /
+        ``shard`` split the rows into contiguous blocks exactly like ``sample``: rows are independent, so there is no
+        communication and the result does not depend on the number of GPUs."""
+        if self.nf is None:
+            raise RuntimeError("RealNVP.log_prob_rows: call fit() first")
+        n = X.shape[0]
+        lo, hi = (self._shard_of(n)[:2] if shard else (0, n))
+        devs = list(devices) if devices else [self._device]
+        out = np.empty(hi - lo, dtype=np.float32)
+        pending = []
+        for k, d in enumerate(devs):
+            b0, b1 = lo + ((hi - lo) * k) // len(devs), lo + ((hi - lo) * (k + 1)) // len(devs)
+            if b1 <= b0:
+                continue
+            dev = torch.device("cuda", d) if not isinstance(d, torch.device) else d
+            eng = self.nf._fused() if dev == self._device else self.nf._replica(dev)
+            with torch.cuda.device(dev):
+                Xd = self._to_device(X[b0:b1], dev)
+                Cd = None if C is None else self._to_device(C[b0:b1], dev)
+                lp = eng.forward(Xd, Cd, want_z=False, want_logdet=False)[2]
+                host = torch.empty(lp.shape, dtype=torch.float32, pin_memory=True)
+                host.copy_(lp, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            pending.append((b0 - lo, b1 - lo, host, ev, lp))
+        for a, b, host, ev, _ in pending:
+            ev.synchronize()
+            out[a:b] = host.numpy()
+        return out

@@ -1,0 +1,114 @@
+"""Oracle parity of the FIT path at the configurations bench.py times (run on the B200 box with ``-m gpu``).
+
+The tensor-core fit kernels (rnvp_mma_kernel<..,2> + the weight-gradient sweep) are compared here with
+``oracle.loss_and_grads`` / ``oracle.fit`` directly -- not with the library's own FP32 kernels -- on full-size batches:
+148 persistent CTAs x 2 row-tile pairs, ring-phase wrap-around, the int64 row gather, ragged tails.
+
+Tolerances: loss rel 1e-5 (north_star's fp32 bound); gradients 2e-5 * max|grad| because the
+packed accumulator is filled with red.global.add in a run-dependent order over up to 75,776 rows (the reference's own
+fp32-vs-fp64 gradient noise is 2.6e-6); loss histories rtol 2e-5 (error compounds over Adam steps).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import realnvp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+C3 = (32, 8, 16, (128,))
+C4 = (64, 16, 24, (128,))
+C5 = (128, 32, 8, (512,))
+
+
+def _flow(shape, seed, dev):
+    from probaforms_b200.models import RealNVPLayer, NormalizingFlow
+    D, Cd, L, hidden = shape
+    params = O.init_params(D, Cd, L, hidden, seed=seed)
+    nf = NormalizingFlow([RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, hidden, "tanh") for i in range(L)], prior=None)
+    nf.load_state_dict(params)
+    return nf.to(dev), params
+
+
+def _grad_check(shape, N, n_res, seed, gather, expect_tc_fit):
+    dev = torch.device("cuda:0")
+    D, Cd, L, hidden = shape
+    nf, params = _flow(shape, seed, dev)
+    eng = nf._fused()
+    assert eng.plan_info(0)["kernel_family"] == 2, "tcgen05 path not selected"
+    if expect_tc_fit is not None:
+        assert eng.fit_on_tensor_cores == expect_tc_fit
+    g = torch.Generator().manual_seed(seed + 1)
+    X = torch.randn(n_res, D, generator=g)
+    Cn = torch.randn(n_res, Cd, generator=g)
+    idx = torch.randint(0, n_res, (N,), generator=g) if gather else None
+    Xd, Cd_ = X.to(dev), Cn.to(dev)
+    eng.zero_grads()
+    lp = torch.empty(N, device=dev)
+    eng.backward(Xd, Cd_, idx.to(dev) if gather else None, N, -1.0 / N, logp_rows=lp)
+    got = eng.unpack_grads().cpu()
+    loss = -float(eng.loss_slot) / N
+    eng.zero_grads()
+    Xb, Cb = (X[idx], Cn[idx]) if gather else (X[:N], Cn[:N])
+    loss_ref, grads_ref = O.loss_and_grads(Xb, Cb, params, L, len(hidden), "tanh")
+    assert abs(loss - float(loss_ref)) < 1e-5 * abs(float(loss_ref)), (loss, float(loss_ref))
+    _, _, lpr = O.flow_forward_rows(Xb, Cb, params, L, len(hidden), "tanh")
+    assert float((lp.cpu() - lpr).abs().max()) < 1e-5 * float(lpr.abs().max())
+    ref = torch.cat([grads_ref[k].reshape(-1) for k in O.param_order(L, len(hidden))])
+    gmax = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    assert err < 2e-5 * gmax, (err, gmax)
+    assert torch.equal(got == 0, ref == 0) or int((got != 0).sum()) <= int((ref != 0).sum())   # masked entries: exact zeros
+
+
+def test_c3_fit_gradients_at_the_benchmarked_batch_with_gather():
+    """75,776 gathered rows = 148 CTAs x 2 pairs of 128-row tiles: the exact launch bench.py times."""
+    _grad_check(C3, 75776, 200000, seed=11, gather=True, expect_tc_fit=True)
+
+
+def test_c3_fit_gradients_ragged_batch():
+    """70,001 rows: CTAs with one and with two pairs, a partial last tile, no gather."""
+    _grad_check(C3, 70001, 70001, seed=12, gather=False, expect_tc_fit=True)
+
+
+def test_c4_fit_gradients_with_gather():
+    _grad_check(C4, 32768 + 77, 60000, seed=13, gather=True, expect_tc_fit=None)
+
+
+def _fit_check(shape, n, bs, epochs, seed, **kw):
+    from probaforms_b200.models import RealNVP
+    D, Cd, L, hidden = shape
+    g = torch.Generator().manual_seed(seed + 7)
+    X = torch.randn(n, D, generator=g).double().numpy()          # the reference's input contract: numpy float64
+    Cn = torch.randn(n, Cd, generator=g).double().numpy()
+    torch.manual_seed(seed)
+    model = RealNVP(n_layers=L, hidden=hidden, batch_size=bs, n_epochs=epochs, lr=1e-3, **kw)
+    model.fit(X, Cn)
+    hist = np.array([float(l) for l in model.loss_history])
+    torch.manual_seed(seed)
+    params = O.init_params(D, Cd, L, hidden)
+    ref_hist, _ = O.fit(X, Cn, params, L, len(hidden), "tanh", bs, epochs, 1e-3)
+    ref_hist = np.array([float(l) for l in ref_hist])
+    assert hist.shape == ref_hist.shape
+    assert np.allclose(hist, ref_hist, rtol=2e-5, atol=2e-6), np.abs(hist - ref_hist).max()
+    for k, v in model.nf.state_dict().items():
+        assert float((v.cpu() - params[k]).abs().max()) < 5e-5 * max(1.0, float(params[k].abs().max())), k
+    return model
+
+
+def test_c3_fit_through_the_api_matches_oracle_fit():
+    """RealNVP.fit on a D=32/H=128 flow (tensor-core fit kernels), 2 epochs with a ragged last batch, vs oracle.fit
+    (the analogue of realnvp.py:236-254): same init, same epoch permutations, same loss trajectory and weights."""
+    m = _fit_check(C3, 3000, 700, 2, seed=21)
+    assert m.nf._fused().fit_on_tensor_cores
+
+
+def test_c3_fit_streamed_ingestion_is_the_same_trajectory():
+    """ingest='stream' (rows of each step gathered on the host and uploaded one step ahead) must not change a bit of
+    the batch composition: compare with the oracle like the resident mode."""
+    m = _fit_check(C3, 3000, 700, 2, seed=22, ingest="stream")
+    assert getattr(m, "h2d_bytes_last_fit", 0) == 2 * 3000 * 40 * 4
+
+
+def test_c4_fit_through_the_api_matches_oracle_fit():
+    _fit_check(C4, 1500, 400, 1, seed=23)

@@ -1,0 +1,150 @@
+"""In-kernel prior draws (rnvp_sample), sharded sampling / log-density and the ingestion paths (``-m gpu``)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import realnvp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(2, 1, 8, (10,)), (32, 8, 4, (64,)), (64, 16, 3, (32,)), (7, 0, 5, (16, 12)), (5, 3, 4, (10,))]
+
+
+def _flow(shape, seed, dev):
+    from probaforms_b200.models import RealNVPLayer, NormalizingFlow
+    D, Cd, L, hidden = shape
+    params = O.init_params(D, Cd, L, hidden, seed=seed)
+    nf = NormalizingFlow([RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, hidden, "tanh") for i in range(L)], prior=None)
+    nf.load_state_dict(params)
+    return nf.to(dev), params
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_in_kernel_noise_matches_the_philox_oracle(shape):
+    """sample(C, seed) == oracle inverse pass on oracle.philox_normal(seed): all three kernel families, ragged N,
+    and a row offset beyond 2^32 (the counter is the 64-bit global row index)."""
+    dev = torch.device("cuda:0")
+    D, Cd, L, hidden = shape
+    nf, params = _flow(shape, 3, dev)
+    for N, off in ((1000, 0), (333, 2 ** 33 + 5)):
+        g = torch.Generator().manual_seed(N)
+        Cn = torch.randn(N, Cd, generator=g) if Cd else None
+        got = nf.sample(Cn.to(dev) if Cd else N, seed=1234567890123, row_offset=off).cpu()
+        eps = O.philox_normal(1234567890123, off, N, D)
+        want = O.flow_sample_from_noise(eps, Cn, params, L, len(hidden), "tanh")
+        assert float((got - want).abs().max()) < 1e-5 * float(want.abs().max())
+        # and against the same library's parity mode on the oracle's noise: the noise itself agrees to fp32 rounding
+        same = nf.sample_from_noise(eps.to(dev), Cn.to(dev) if Cd else None).cpu()
+        assert float((got - same).abs().max()) < 2e-6 * float(want.abs().max())
+
+
+def test_sampling_is_independent_of_the_sharding():
+    """Row blocks sampled separately (as different GPUs would) are exactly the rows of the single request."""
+    dev = torch.device("cuda:0")
+    nf, _ = _flow((32, 8, 4, (64,)), 5, dev)
+    N = 5000
+    Cn = torch.randn(N, 8, device=dev)
+    whole = nf.sample(Cn, seed=99)
+    parts = [nf.sample(Cn[a:b].contiguous(), seed=99, row_offset=a) for a, b in ((0, 1234), (1234, 1235), (1235, N))]
+    assert torch.equal(torch.cat(parts), whole)
+    torch.manual_seed(4)
+    a = nf.sample(Cn)
+    torch.manual_seed(4)
+    assert torch.equal(nf.sample(Cn), a)                      # default seed comes from torch's global generator
+    assert not torch.equal(nf.sample(Cn), a)
+
+
+def test_model_sample_devices_and_log_prob_rows():
+    from probaforms_b200.models import RealNVP
+    rng = np.random.default_rng(2)
+    X, Cn = rng.normal(size=(3000, 6)), rng.normal(size=(3000, 2))
+    torch.manual_seed(0)
+    m = RealNVP(n_layers=4, hidden=(16,), n_epochs=1, batch_size=512)
+    m.fit(X, Cn)
+    one = m.sample(Cn, seed=5)
+    assert one.shape == (3000, 6) and one.dtype == np.float32
+    devs = list(range(min(torch.cuda.device_count(), 2))) * (2 if torch.cuda.device_count() < 2 else 1)
+    assert np.array_equal(m.sample(Cn, seed=5, devices=devs), one)              # blocks on (possibly) several GPUs
+    assert np.array_equal(m.sample(Cn, seed=5, shard=True), one)                # no process group: the whole request
+    many = m.sample(Cn, seed=5, n_draws=3)
+    assert many.shape == (3, 3000, 6) and np.array_equal(many[0], one) and not np.array_equal(many[1], one)
+    lp = m.log_prob_rows(X, Cn)
+    ref = m.nf.log_prob_rows(torch.as_tensor(X, dtype=torch.float32).cuda(), torch.as_tensor(Cn, dtype=torch.float32).cuda())
+    assert np.array_equal(lp, ref.cpu().numpy())
+    assert np.array_equal(m.log_prob_rows(X, Cn, devices=devs), lp)
+    big = m.sample(np.repeat(Cn, 200, axis=0), seed=6)                           # > 1 MB: the chunked pinned egress path
+    assert big.shape == (600000, 6) and np.isfinite(big).all()
+    assert np.array_equal(big[:3000:1][:5], m.sample(np.repeat(Cn, 200, axis=0)[:5], seed=6))
+
+
+def test_fit_validates_inputs_like_the_reference():
+    from probaforms_b200.models import RealNVP
+    rng = np.random.default_rng(0)
+    X, Cn = rng.normal(size=(100, 4)), rng.normal(size=(100, 2))
+    m = RealNVP(n_epochs=1)
+    with pytest.raises(ValueError):
+        m.fit(X, Cn[:50])                       # TensorDataset: "Size mismatch between tensors"
+    m = RealNVP(n_epochs=1)
+    m.fit(X, Cn)
+    with pytest.raises(ValueError):
+        m.fit(X[:, :3], Cn)                     # warm start with another width
+    with pytest.raises(ValueError):
+        m.fit(X, None)
+    with pytest.raises(ValueError):
+        m.fit(X, Cn[:99])
+    m.fit(X.astype(np.float32), torch.as_tensor(Cn))      # mixed containers are fine
+
+
+def test_checkpoint_resume_continues_the_adam_trajectory():
+    """state_dict of model + optimiser -> fresh objects -> continued fit equals an uninterrupted one (moments and
+    step count are imported back into the engine); deepcopy of a fitted model keeps training too."""
+    from probaforms_b200.models import RealNVP
+    rng = np.random.default_rng(1)
+    X, Cn = rng.normal(size=(256, 5)), rng.normal(size=(256, 3))
+
+    def run(n_fits, seed_each):
+        torch.manual_seed(0)
+        m = RealNVP(n_layers=4, hidden=(8,), n_epochs=2, batch_size=64, lr=1e-2)
+        for k in range(n_fits):
+            torch.manual_seed(seed_each + k)
+            m.fit(X, Cn)
+        return m
+
+    full = run(2, 100)
+    half = run(1, 100)
+    sd_model, sd_opt = copy.deepcopy(half.state_dict()), copy.deepcopy(half.opt.state_dict())
+    torch.manual_seed(0)
+    fresh = RealNVP(n_layers=4, hidden=(8,), n_epochs=2, batch_size=64, lr=1e-2)
+    fresh._model_init(X, Cn)
+    fresh.load_state_dict(sd_model)
+    fresh.opt.load_state_dict(sd_opt)
+    torch.manual_seed(101)
+    fresh.fit(X, Cn)
+    for (k, a), (_, b) in zip(full.nf.state_dict().items(), fresh.nf.state_dict().items()):
+        assert torch.equal(a, b), k
+    clone = copy.deepcopy(half)
+    torch.manual_seed(101)
+    clone.fit(X, Cn)
+    for (k, a), (_, b) in zip(full.nf.state_dict().items(), clone.nf.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_upload_paths_agree():
+    """numpy float64, numpy float32, pageable and pinned torch rows all land as the same float32 device rows, including
+    the chunked double-buffered path for sets above 1 MB."""
+    from probaforms_b200 import _lib
+    from probaforms_b200.ingest import upload_resident, rows_to_numpy
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(400001, 9))
+    want = torch.as_tensor(A, dtype=torch.float32)
+    for src in (A, A.astype(np.float32), want.clone(), want.clone().pin_memory(), torch.as_tensor(A)):
+        got = upload_resident(lib, src, dev, chunk_bytes=1 << 20)
+        torch.cuda.synchronize()
+        assert got.dtype == torch.float32 and torch.equal(got.cpu(), want)
+    back = rows_to_numpy(lib, got, chunk_bytes=1 << 20)
+    assert back.dtype == np.float32 and np.array_equal(back, want.numpy())
