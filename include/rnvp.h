@@ -123,7 +123,7 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
  * rec = rnvp_wgrad_record_floats(d) floats per (layer, row):
  * h [2][H] (nn_t | nn_s) | u = [x_K, c, 0..] (ceil8(D/2+Cd)) | delta2 [2][D/2],
  * stored in blocks of 32 rows as d_records[L][Npad/32][rec/4][32][4]: float4 column group q of row r of a block sits
- * in slot (r ^ (q & 1)).  Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.
+ * in slot (r ^ (q & 7)).  Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.
  * tcgen05-eligible flows with D = 32, H <= 128. */
 int rnvp_wgrad_record_floats(const rnvp_desc* d);
 int rnvp_wgrad_sweep(const rnvp_desc* d, const float* d_packed, int64_t Npad, const float* d_records, float* d_gpacked,

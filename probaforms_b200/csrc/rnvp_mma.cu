@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
                 float* hb = rec_base(i) + (((q0 / CU) * H + cc * CU) >> 2) * 128;
 #pragma unroll
                 for (int m = 0; m < 8; ++m)
-                  *reinterpret_cast<float4*>(hb + m * 128 + ((lane ^ (m & 1)) << 2)) =
+                  *reinterpret_cast<float4*>(hb + m * 128 + ((lane ^ (m & a.rec_swz)) << 2)) =
                       make_float4(__uint_as_float(r[4 * m]), __uint_as_float(r[4 * m + 1]), __uint_as_float(r[4 * m + 2]),
                                   __uint_as_float(r[4 * m + 3]));
               }
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
             float* recb = rec_base(i);
             auto rec_st = [&](int col, float4 v) {
               const int cg = col >> 2;
-              *reinterpret_cast<float4*>(recb + cg * 128 + ((lane ^ (cg & 1)) << 2)) = v;
+              *reinterpret_cast<float4*>(recb + cg * 128 + ((lane ^ (cg & a.rec_swz)) << 2)) = v;
             };
             // ---- x_T and s of this layer from the forward stash; delta2 and the new g_T
             uint32_t e2h[2 * DH], e2l[2 * DH];
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) rnvp_mma_kernel(const __grid_c
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                   const int cg = (net * H + 16 * hc) / 4 + m;
-                  const float4 v = *reinterpret_cast<const float4*>(recb + cg * 128 + ((lane ^ (cg & 1)) << 2));
+                  const float4 v = *reinterpret_cast<const float4*>(recb + cg * 128 + ((lane ^ (cg & a.rec_swz)) << 2));
                   pa_h[16 * net + 4 * m] = __float_as_uint(v.x); pa_h[16 * net + 4 * m + 1] = __float_as_uint(v.y);
                   pa_h[16 * net + 4 * m + 2] = __float_as_uint(v.z); pa_h[16 * net + 4 * m + 3] = __float_as_uint(v.w);
                 }

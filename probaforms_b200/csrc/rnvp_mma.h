@@ -25,6 +25,7 @@ struct RnvpMmaArgs {
   float scale;                 // d(out)/d(logp_row): g_logdet = scale, g_z = -scale*z
   float* records;
   int rec;
+  int rec_swz;                 // slot swizzle mask of the record blocks: 7 (tcgen05 weight-gradient sweep) or 1 (mma.sync sweep)
   long long Npad;
   long long* trace;            // development aid (rnvp_debug_set_trace): CTA 0 logs (tag, clock64) pairs of the backward sweep
   int wt_floats;               // floats of one transposed image (W2T, then W1T) per layer; 0 unless do_bwd

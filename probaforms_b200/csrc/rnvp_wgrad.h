@@ -19,3 +19,18 @@ struct RnvpWgradArgs {
   int n_slices;                    // row slices per layer; grid = L * n_slices
   int H;
 };
+
+// Arguments of the tcgen05 weight-gradient sweep (rnvp_wgrad_tc.cu): records as above but with the 3-bit slot swizzle,
+// [L][Npad/32][rec/4][32 slots][4], slot = row ^ (column group & 7)
+struct RnvpWgradTcArgs {
+  const float* gR;
+  int rec;                         // floats per record = 2H + K1P8 + 2*TP
+  long long Npad;                  // rows, multiple of 32; padding rows hold zeros in delta2
+  int H, K1P8, K1, TP, nT;         // hidden width; u columns (padded to 8 / real); delta2 columns per net (stored / real)
+  int n_slices, n_mblocks;         // grid = L * n_mblocks * n_slices; n_mblocks = ceil(2H / 128)
+  float* gpacked;
+  const float* packed;
+  int act;
+  const RnvpWgradLayer* layers;
+};
+size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, int K1P8);

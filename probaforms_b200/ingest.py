@@ -58,8 +58,20 @@ def gather_into(lib, arr, idx, row0, n, dst, threads=None):
         raise RuntimeError(f"rnvp_host_gather_rows failed (code {rc})")
 
 
-def _pinned(shape, dtype=torch.float32):
-    return torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+_STAGING = {}     # key -> flat pinned float32 buffer, grown on demand and kept for the life of the process
+
+
+def _pinned(shape, key=None):
+    """Pinned float32 staging buffer of the given shape.  cudaHostAlloc costs about a millisecond per megabyte, so
+    buffers are cached per ``key`` (role, slot) and reused by every later fit / sample call of the process."""
+    numel = int(np.prod(shape))
+    if key is None:
+        return torch.empty(shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    buf = _STAGING.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(max(numel, 1), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        _STAGING[key] = buf
+    return buf[:numel].view(shape)
 
 
 def upload_resident(lib, A, dev, chunk_bytes=32 << 20):
@@ -82,7 +94,7 @@ def upload_resident(lib, A, dev, chunk_bytes=32 << 20):
         gather_into(lib, arr, None, 0, n, stage, threads=1)
         out.copy_(stage)
         return out
-    stage = [_pinned((rows, w)), _pinned((rows, w))]
+    stage = [_pinned((rows, w), ("up", 0)), _pinned((rows, w), ("up", 1))]
     done = [None, None]
     copy_stream = torch.cuda.Stream(device=dev)
     for k, r0 in enumerate(range(0, n, rows)):
@@ -113,7 +125,7 @@ def rows_to_numpy(lib, t, chunk_bytes=32 << 20):
     flat = t.view(-1)
     n = flat.numel()
     per = max(1, chunk_bytes // 4)
-    stage = [_pinned((min(per, n),)), _pinned((min(per, n),))]
+    stage = [_pinned((min(per, n),), ("down", 0)), _pinned((min(per, n),), ("down", 1))]
     evs = [None, None]
     dev = t.device
     copy_stream = torch.cuda.Stream(device=dev)
@@ -152,8 +164,8 @@ class StepStreamer:
         self.lib, self.dev = lib, dev
         self.X, self.Cn = host_rows(X), (host_rows(Cn) if Cn is not None else None)
         w, wc = self.X.shape[1], (self.Cn.shape[1] if self.Cn is not None else 0)
-        self.hx = [_pinned((max_rows, w)) for _ in range(self.SLOTS)]
-        self.hc = [_pinned((max_rows, wc)) for _ in range(self.SLOTS)] if wc else None
+        self.hx = [_pinned((max_rows, w), ("sx", k)) for k in range(self.SLOTS)]
+        self.hc = [_pinned((max_rows, wc), ("sc", k)) for k in range(self.SLOTS)] if wc else None
         self.dx = [torch.empty(max_rows, w, dtype=torch.float32, device=dev) for _ in range(self.SLOTS)]
         self.dc = [torch.empty(max_rows, wc, dtype=torch.float32, device=dev) for _ in range(self.SLOTS)] if wc else None
         self.free = [None] * self.SLOTS            # event: the step that used the slot has finished

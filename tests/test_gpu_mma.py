@@ -91,14 +91,16 @@ def test_fit_steps_on_tcgen05_path_track_fp32_path():
     assert torch.allclose(curves[0], curves[1], rtol=1e-4, atol=1e-4), (curves[0], curves[1])
 
 
-def test_wgrad_sweep_through_the_abi_matches_fp64():
+@pytest.mark.parametrize("H,N", [(64, 2048), (128, 4096 + 32), (96, 960), (32, 64)])
+def test_wgrad_sweep_through_the_abi_matches_fp64(H, N):
     """rnvp_wgrad_sweep alone (C ABI): blocked records [L][N/32][rec/4][32][4] built on the host side of the ABI, gradients
-    against an fp64 evaluation of dW1 = delta1^T u, dW2 = delta2^T h with delta1 = (delta2 W2) * (1 - h^2)."""
+    against an fp64 evaluation of dW1 = delta1^T u, dW2 = delta2^T h with delta1 = (delta2 W2) * (1 - h^2).  H = 64 puts
+    both nets into one 128-lane block (block-diagonal W2 image), H = 128 gives one block per net, H = 48 / 16 partial blocks."""
     import ctypes as C
     from probaforms_b200 import _lib
     from probaforms_b200.models import RealNVPLayer, NormalizingFlow
     dev = torch.device("cuda:0")
-    D, Cd, L, H, N = 32, 8, 3, 64, 2048
+    D, Cd, L = 32, 8, 3
     K1P = (D // 2 + Cd + 7) // 8 * 8
     torch.manual_seed(0)
     nf = NormalizingFlow([RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, (H,), "tanh") for i in range(L)], None).to(dev)
@@ -112,7 +114,8 @@ def test_wgrad_sweep_through_the_abi_matches_fp64():
     u[:, :, D // 2 + Cd:] = 0
     R = torch.cat([h.reshape(L, N, 2 * H), u, d2.reshape(L, N, D)], dim=2)
     Rb = R.view(L, N // 32, 32, rec // 4, 4).permute(0, 1, 3, 2, 4).contiguous()
-    Rb[:, :, 1::2] = Rb[:, :, 1::2][:, :, :, torch.arange(32, device=dev) ^ 1]       # slot = row ^ (group & 1)
+    for q in range(1, 8):                                                            # slot = row ^ (group & 7)
+        Rb[:, :, q::8] = Rb[:, :, q::8][:, :, :, torch.arange(32, device=dev) ^ q]
     eng.zero_grads()
     P = lambda t: C.c_void_p(t.data_ptr())
     _lib.check(eng.lib.rnvp_wgrad_sweep(eng._desc, P(eng.packed), N, P(Rb), P(eng.gpacked), None), "rnvp_wgrad_sweep")
