@@ -617,7 +617,8 @@ int rnvp_wgrad_sweep(const rnvp_desc* dc, const float* d_packed, int64_t Npad, c
     a.K1P8 = K1P; a.K1 = d->mDH + d->Cd; a.TP = TP; a.nT = d->mDH;
     a.n_mblocks = (2 * d->hidden[0] + 127) / 128;
     a.n_slices = (int)std::max<long long>(1, std::min<long long>(Npad / 32, d->num_sms / (d->L * a.n_mblocks)));
-    a.gpacked = d_gpacked; a.packed = d_packed; a.act = d->act; a.layers = d->d_wg;
+    a.gpacked = d_gpacked; a.packed = d_packed; a.act = d->act; a.layers = d->d_wg; a.trace = g_mma_trace;
+    { const char* o = getenv("RNVP_WG_ONE_ISSUER"); a.one_issuer = (o && atoi(o)) ? 1 : 0; }
     const int NU = (K1P + 15) & ~15;
     cudaError_t e = rnvp_launch_wgrad_tc(NU, TP, a, d->L * a.n_mblocks * a.n_slices, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "rnvp_wgrad_tc_kernel");

@@ -8,11 +8,11 @@
 // tcgen05.mma contracts over the COLUMNS of its A operand (TMEM lane = output row), so this kernel works in the transposed
 // world: one TMEM lane per HIDDEN UNIT.  A CTA owns (layer, block of 128 units of the concatenated list [nn_t | nn_s], row
 // slice) and streams its rows in stages of 32:
-//   warp 0      TMA producer: three bulk copies per stage (this block's h columns, u, delta2) into a raw ring
+//   warp 12     TMA producer: three bulk copies per stage (this block's h columns, u, delta2) into a raw ring
 //   warps 2-3   converters: u and delta2 -> K-major operand tiles with K = rows (a 4-byte transposing scatter, conflict
 //               free through a padded K-group stride), TF32 hi (the raw fp32: the tensor core reads its upper 19 bits) and
 //               lo = v - trunc(v); delta2 also as the [rows x e] operand of the dh product; db2 partial sums in registers
-//   warp 1      MMA issuer (one elected lane): dh^T[unit][row] = W2^T-image (TMEM, loaded once) x delta2  (3-pass split);
+//   warps 0-1   MMA issuers (one elected lane each; warp 0: dh^T and dW1, warp 1: dW2): dh^T[unit][row] = W2^T-image (TMEM, loaded once) x delta2  (3-pass split);
 //               then dW1 += delta1^T (TMEM) x u and dW2^T += h^T (TMEM) x delta2, main products and split corrections in
 //               separate TMEM accumulators
 //   warps 4-11  unit owners (two threads per TMEM lane = hidden unit, 16 of the stage's 32 rows each): dh^T from TMEM, h
@@ -30,6 +30,7 @@
 // kernel are bank-conflict free.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "rnvp_wgrad.h"
 #include "tc05.cuh"
 
@@ -37,48 +38,73 @@ namespace {
 using namespace tc05;
 
 constexpr int WT_ROWS = 32;                 // rows per stage = rows per record block = K of one stage's gradient products
-constexpr int WT_THREADS = 384;             // warp 0 producer, 1 issuer, 2-3 converters, 4-11 unit owners
+constexpr int WT_THREADS = 416;             // warps 0-1 issuers, 2-3 converters, 4-11 unit owners, 12 TMA producer
 constexpr int WT_KG = 36;                   // floats between K-groups (4 rows) of a K-major-over-rows tile: 144 B, so that the
                                             // transposing 4-byte stores of a warp (lanes = rows) hit 32 different banks
 constexpr int WT_NG = 8 * WT_KG;            // floats between 8-column groups (SBO = 1152 B)
 constexpr int WT_FOLD = 4;                  // stages per accumulator chain (16 accumulations of K = 8)
 
+// Wait accounting (development aid, rnvp_debug_set_trace): when a trace buffer is set, every role of CTA 0 sums the cycles
+// it spends in each of its mbarrier waits and writes the totals at the end: trace[role * 8 + k] (role 0 issuer A, 1 issuer
+// B, 2 converter warp 2, 3 owner warp 4, 4 producer; k = wait site, 7 = total cycles of the role's loop).
+struct WaitAcc {
+  long long t[8];
+  bool on;
+  __device__ __forceinline__ void init(bool enable) { on = enable; for (int k = 0; k < 8; ++k) t[k] = 0; }
+  __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, int k, bool relaxed = false) {
+    if (!on) {
+      if (relaxed) tc05::mbar_wait_relaxed(bar, parity);
+      else tc05::mbar_wait(bar, parity);
+      return;
+    }
+    const long long t0 = clock64();
+    if (relaxed) tc05::mbar_wait_relaxed(bar, parity);
+    else tc05::mbar_wait(bar, parity);
+    t[k] += clock64() - t0;
+  }
+  __device__ __forceinline__ void flush(long long* out, int role, long long total) {
+    if (!on) return;
+    t[7] = total;
+    for (int k = 0; k < 8; ++k) out[role * 8 + k] = t[k];
+  }
+};
+
 __device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// NU: columns of the dW1 tile (>= K1P8, multiple of 16); TP: delta2 columns per net (multiple of 16)
+// NU: columns of the dW1 tile (>= K1P8, multiple of 16); K1P8: u columns of a record; TP: delta2 columns per net (multiple of 16)
 // NBUF: TMEM staging buffers; NOP: operand buffers in shared memory; NSLOT: raw ring depth
-template <int NU, int TP, int NBUF, int NOP, int NSLOT>
+template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT>
 __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __grid_constant__ RnvpWgradTcArgs a) {
   // TMEM column map.  Per net the gradient accumulators sit side by side, [main | corr]: A_hi x [B_hi ; B_lo] is ONE MMA of
   // twice the width (the hi and lo operand tiles are adjacent in shared memory), A_lo x B_hi adds into the corr half.
   constexpr int W2H = 0, W2L = 2 * TP, STG0 = 4 * TP, STGW = 128;               // staging: DH/D1H +0, D1L +32, HH +64, HL +96
   constexpr int ACC1 = STG0 + NBUF * STGW, ACC2 = ACC1 + 2 * NU, TCOLS = ACC2 + 4 * TP;
   static_assert(TCOLS <= 512, "TMEM budget");
-  static_assert(NU % 16 == 0 && TP % 16 == 0, "N of an M=128 MMA is a multiple of 16");
+  static_assert(NU % 16 == 0 && TP % 16 == 0 && K1P8 % 8 == 0 && K1P8 <= NU, "N of an M=128 MMA is a multiple of 16");
   constexpr int UB = (NU / 8) * WT_NG, EBN = (TP / 8) * WT_NG, DK = WT_ROWS * 2 * TP;   // floats of one hi (or lo) tile
   constexpr int OPF = 2 * UB + 4 * EBN + 2 * DK;                                  // floats of one operand buffer
   // operand buffer: [u_hi | u_lo | e_t_hi | e_t_lo | e_s_hi | e_s_lo | dk_hi | dk_lo]
+  constexpr int RAW_H = WT_ROWS * 128, RAW_U = WT_ROWS * K1P8, RAW_E = WT_ROWS * 2 * TP, RAW = RAW_H + RAW_U + RAW_E;
 
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = a.H, H2 = 2 * H, K1P8 = a.K1P8;
+  const int H = a.H, H2 = 2 * H;
   const int per_layer = a.n_mblocks * a.n_slices;
   const int layer = blockIdx.x / per_layer, rem = blockIdx.x - layer * per_layer;
   const int mb = rem / a.n_slices, slice = rem - mb * a.n_slices;
   const int ncols_h = min(128, H2 - 128 * mb);                  // this block's hidden units (h columns 128*mb ..)
   const int net_lo = (128 * mb >= H) ? 1 : 0, net_hi = (128 * mb + ncols_h > H) ? 1 : 0;   // nets present in this lane block
-  const int raw_h = WT_ROWS * 128, raw_u = WT_ROWS * K1P8, raw_e = WT_ROWS * 2 * TP;
-  const int raw_floats = raw_h + raw_u + raw_e;
   float* raw = sm;
-  float* op = sm + NSLOT * raw_floats;
+  float* op = sm + NSLOT * RAW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(op + NOP * OPF);
   uint64_t* b_full = bars;                    // [NSLOT] raw slot filled (TMA bytes)
   uint64_t* b_empty = b_full + NSLOT;         // [NSLOT] raw slot drained: 2 converter warps + 8 owner warps
   uint64_t* b_conv = b_empty + NSLOT;         // [NOP]   operand buffer converted (64 threads)
-  uint64_t* b_opfree = b_conv + NOP;          // [NOP]   gradient MMAs of the stage done (tcgen05.commit)
-  uint64_t* b_dh = b_opfree + NOP;            // [NBUF]  dh^T ready (commit)
-  uint64_t* b_afull = b_dh + NBUF;            // [NBUF]  delta1^T / h^T staged in TMEM (256 owner threads)
-  uint64_t* b_accfull = b_afull + NBUF;       // [1]     an accumulator chain is complete (commit)
+  uint64_t* b_opfree = b_conv + NOP;          // [NOP]   gradient MMAs of the stage done (one tcgen05.commit per issuer)
+  uint64_t* b_dh = b_opfree + NOP;            // [NBUF]  dh^T ready, and the dW1 products that read this staging buffer done
+  uint64_t* b_hfree = b_dh + NBUF;            // [NBUF]  the dW2 products that read this staging buffer done
+  uint64_t* b_afull = b_hfree + NBUF;         // [NBUF]  delta1^T / h^T staged in TMEM (256 owner threads)
+  uint64_t* b_accfull = b_afull + NBUF;       // [1]     an accumulator chain is complete (one commit per issuer)
   uint64_t* b_accfree = b_accfull + 1;        // [1]     ... and drained into registers (256 owner threads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_accfree + 1);
 
@@ -86,12 +112,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
   const long long blk0 = blocks_total * slice / a.n_slices, blk1 = blocks_total * (slice + 1) / a.n_slices;
   const int nst = (int)(blk1 - blk0);                            // stages of this CTA
 
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 10); }
-    for (int b = 0; b < NOP; ++b) { mbar_init(&b_conv[b], 64); mbar_init(&b_opfree[b], 1); }
-    for (int b = 0; b < NBUF; ++b) { mbar_init(&b_dh[b], 1); mbar_init(&b_afull[b], 256); }
-    mbar_init(b_accfull, 1); mbar_init(b_accfree, 256);
+    for (int b = 0; b < NOP; ++b) { mbar_init(&b_conv[b], 64); mbar_init(&b_opfree[b], a.one_issuer ? 1 : 2); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&b_dh[b], 1); mbar_init(&b_hfree[b], 1); mbar_init(&b_afull[b], 256); }
+    mbar_init(b_accfull, a.one_issuer ? 1 : 2); mbar_init(b_accfree, 256);
     mbar_fence_init();
   }
   // zero the operand buffers once: padding columns (K1P8..NU) and padding K-groups are never written again
@@ -103,30 +129,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
   const uint32_t tbase = *tmem_slot;
   const size_t block_floats = (size_t)WT_ROWS * a.rec;
   const float* gblk = a.gR + ((size_t)layer * blocks_total + blk0) * block_floats;
+  auto desc = [](uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) { return smem_desc_kmajor_nosw(addr, lbo_bytes, sbo_bytes); };
+  constexpr uint32_t LBO = WT_KG * 4u, SBO = WT_NG * 4u, KS = 2 * WT_KG * 4u;      // K-major-over-rows tiles: one K step = 8 rows = 2 K-groups
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint32_t bytes_h = (uint32_t)(WT_ROWS * ncols_h) * 4u, bytes_u = (uint32_t)raw_u * 4u, bytes_e = (uint32_t)raw_e * 4u;
-      for (int s = 0; s < nst; ++s) {
-        const int slot = s % NSLOT;
-        if (s >= NSLOT) mbar_wait(&b_empty[slot], (uint32_t)((s / NSLOT - 1) & 1));
-        const float* src = gblk + (size_t)s * block_floats;
-        float* dst = raw + slot * raw_floats;
-        mbar_expect_tx(&b_full[slot], bytes_h + bytes_u + bytes_e);
-        bulk_g2s(dst, src + (size_t)WT_ROWS * 128 * mb, bytes_h, &b_full[slot]);
-        bulk_g2s(dst + raw_h, src + (size_t)WT_ROWS * H2, bytes_u, &b_full[slot]);
-        bulk_g2s(dst + raw_h + raw_u, src + (size_t)WT_ROWS * (H2 + K1P8), bytes_e, &b_full[slot]);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ issuer A: dh^T and dW1
     asm volatile("bar.sync 1, 288;" ::: "memory");             // the owners have staged the W2^T image in TMEM
     fence_after_sync();
     const bool leader = elect_one();
     const uint32_t idesc_dh = idesc_tf32(128, WT_ROWS), idesc_u = idesc_tf32(128, NU), idesc_u2 = idesc_tf32(128, 2 * NU);
-    const uint32_t idesc_e = idesc_tf32(128, TP), idesc_e2 = idesc_tf32(128, 2 * TP);
-    auto desc = [](uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) { return smem_desc_kmajor_nosw(addr, lbo_bytes, sbo_bytes); };
     const uint32_t op_addr = smem_u32(op);
     const int kj0 = net_lo * (TP / 8), kj1 = (net_hi + 1) * (TP / 8);     // K steps of the dh product that are not all-zero
     // dh^T of stage s -> staging buffer s % NBUF: A = W2^T image (TMEM), B = delta2 [N = rows, K = 2TP] (core-matrix tiled)
@@ -134,16 +145,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
       const int b = s % NBUF, ob = s % NOP;
       const uint32_t dk_hi = op_addr + (uint32_t)(ob * OPF + 2 * UB + 4 * EBN) * 4u, dk_lo = dk_hi + (uint32_t)DK * 4u;
       const uint32_t d = tbase + STG0 + b * STGW;
-      constexpr uint32_t SBO = (2 * TP / 4) * 128u;
-      for (int j = kj0; j < kj1; ++j) mma_tf32_ts(d, tbase + W2L + 8 * j, desc(dk_hi + 256u * j, 128u, SBO), idesc_dh, j > kj0 ? 1u : 0u);
-      for (int j = kj0; j < kj1; ++j) mma_tf32_ts(d, tbase + W2H + 8 * j, desc(dk_lo + 256u * j, 128u, SBO), idesc_dh, 1u);
-      for (int j = kj0; j < kj1; ++j) mma_tf32_ts(d, tbase + W2H + 8 * j, desc(dk_hi + 256u * j, 128u, SBO), idesc_dh, 1u);
+      constexpr uint32_t SBOD = (2 * TP / 4) * 128u;
+#pragma unroll
+      for (int j = 0; j < 2 * TP / 8; ++j)
+        if (j >= kj0 && j < kj1) mma_tf32_ts(d, tbase + W2L + 8 * j, desc(dk_hi + 256u * j, 128u, SBOD), idesc_dh, j > kj0 ? 1u : 0u);
+#pragma unroll
+      for (int j = 0; j < 2 * TP / 8; ++j)
+        if (j >= kj0 && j < kj1) mma_tf32_ts(d, tbase + W2H + 8 * j, desc(dk_lo + 256u * j, 128u, SBOD), idesc_dh, 1u);
+#pragma unroll
+      for (int j = 0; j < 2 * TP / 8; ++j)
+        if (j >= kj0 && j < kj1) mma_tf32_ts(d, tbase + W2H + 8 * j, desc(dk_hi + 256u * j, 128u, SBOD), idesc_dh, 1u);
     };
     uint32_t ph_conv = 0, ph_afull = 0, ph_accfree = 0;          // one phase bit per ring entry
-    // prologue: dh^T of the first NBUF stages
-    for (int s = 0; s < NBUF && s < nst; ++s) {
+    WaitAcc wa; wa.init((a.trace != nullptr && blockIdx.x == 0));
+    const long long tstart = clock64();
+    for (int s = 0; s < NBUF && s < nst; ++s) {                  // prologue: dh^T of the first NBUF stages
       const int ob = s % NOP;
-      mbar_wait(&b_conv[ob], (ph_conv >> ob) & 1u); ph_conv ^= 1u << ob;
+      wa.wait(&b_conv[ob], (ph_conv >> ob) & 1u, 0); ph_conv ^= 1u << ob;
       fence_after_sync();
       if (leader) { issue_dh(s); mma_commit(&b_dh[s % NBUF]); }
       __syncwarp();
@@ -151,23 +169,32 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
     for (int s = 0; s < nst; ++s) {
       const int b = s % NBUF, ob = s % NOP;
       const bool first_in_grp = (s % WT_FOLD) == 0, last_in_grp = (s % WT_FOLD) == WT_FOLD - 1 || s == nst - 1;
-      if (first_in_grp && s > 0) { mbar_wait(b_accfree, ph_accfree); ph_accfree ^= 1; }
-      mbar_wait(&b_afull[b], (ph_afull >> b) & 1u); ph_afull ^= 1u << b;
+      if (first_in_grp && s > 0) { wa.wait(b_accfree, ph_accfree, 1); ph_accfree ^= 1; }
+      wa.wait(&b_afull[b], (ph_afull >> b) & 1u, 2); ph_afull ^= 1u << b;
       fence_after_sync();
       if (leader) {
-        const uint32_t ub = op_addr + (uint32_t)(ob * OPF) * 4u, eb = ub + (uint32_t)(2 * UB) * 4u;
+        const uint32_t ub = op_addr + (uint32_t)(ob * OPF) * 4u;
         const uint32_t stg = tbase + STG0 + b * STGW;
-        constexpr uint32_t LBO = WT_KG * 4u, SBO = WT_NG * 4u, KS = 2 * WT_KG * 4u;      // one K step = 8 rows = 2 K-groups
+        const long long tq0 = wa.on ? clock64() : 0;
 #pragma unroll
         for (int j = 0; j < WT_ROWS / 8; ++j) {
-          const uint32_t acc = (first_in_grp && j == 0) ? 0u : 1u;
-          mma_tf32_ts(tbase + ACC1, stg + 0 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u2, acc);          // d1_hi x [u_hi ; u_lo]
-          mma_tf32_ts(tbase + ACC1 + NU, stg + 32 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u, 1u);       // d1_lo x u_hi
-          for (int n = net_lo; n <= net_hi; ++n) {
-            const uint32_t ebn = eb + (uint32_t)(n * 2 * EBN) * 4u, d2 = tbase + ACC2 + n * 2 * TP;
-            mma_tf32_ts(d2, stg + 64 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e2, acc);                  // h_hi x [e_hi ; e_lo]
-            mma_tf32_ts(d2 + TP, stg + 96 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e, 1u);               // h_lo x e_hi
+          mma_tf32_ts(tbase + ACC1, stg + 0 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u2, (first_in_grp && j == 0) ? 0u : 1u);   // d1_hi x [u_hi ; u_lo]
+          mma_tf32_ts(tbase + ACC1 + NU, stg + 32 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u, 1u);                               // d1_lo x u_hi
+        }
+        if (wa.on) wa.t[4] += clock64() - tq0;
+        if (a.one_issuer) {
+          const uint32_t eb = ub + (uint32_t)(2 * UB) * 4u;
+          const uint32_t idesc_e = idesc_tf32(128, TP), idesc_e2 = idesc_tf32(128, 2 * TP);
+#pragma unroll
+          for (int j = 0; j < WT_ROWS / 8; ++j) {
+            const uint32_t acc = (first_in_grp && j == 0) ? 0u : 1u;
+            for (int n = net_lo; n <= net_hi; ++n) {
+              const uint32_t ebn = eb + (uint32_t)(n * 2 * EBN) * 4u, d2 = tbase + ACC2 + n * 2 * TP;
+              mma_tf32_ts(d2, stg + 64 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e2, acc);
+              mma_tf32_ts(d2 + TP, stg + 96 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e, 1u);
+            }
           }
+          mma_commit(&b_hfree[b]);
         }
         mma_commit(&b_opfree[ob]);
         if (last_in_grp) mma_commit(b_accfull);
@@ -175,49 +202,124 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
       __syncwarp();
       if (s + NBUF < nst) {                      // dh^T of the stage that will reuse this staging buffer
         const int ob2 = (s + NBUF) % NOP;
-        mbar_wait(&b_conv[ob2], (ph_conv >> ob2) & 1u); ph_conv ^= 1u << ob2;
+        wa.wait(&b_conv[ob2], (ph_conv >> ob2) & 1u, 0); ph_conv ^= 1u << ob2;
         fence_after_sync();
-        if (leader) { issue_dh(s + NBUF); mma_commit(&b_dh[b]); }
+        if (leader) {
+          const long long tq0 = wa.on ? clock64() : 0;
+          issue_dh(s + NBUF);
+          if (wa.on) wa.t[5] += clock64() - tq0;
+          mma_commit(&b_dh[b]);
+          if (wa.on) wa.t[6] += clock64() - tq0;
+        }
         __syncwarp();
       }
+    }
+    if (leader) wa.flush(a.trace, 0, clock64() - tstart);
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ issuer B: dW2 (issuing, not the tensor pipe, bounds
+    // these small MMAs -- ~35 cycles each -- so the gradient products are split over two issuing threads)
+    const bool leader = elect_one();
+    int nst_b = nst;
+    const uint32_t idesc_e = idesc_tf32(128, TP), idesc_e2 = idesc_tf32(128, 2 * TP);
+    const uint32_t op_addr = smem_u32(op);
+    uint32_t ph_afull = 0, ph_accfree = 0;
+    if (a.one_issuer) nst_b = 0;
+    WaitAcc wa; wa.init((a.trace != nullptr && blockIdx.x == 0));
+    const long long tstart = clock64();
+    for (int s = 0; s < nst_b; ++s) {
+      const int b = s % NBUF, ob = s % NOP;
+      const bool first_in_grp = (s % WT_FOLD) == 0, last_in_grp = (s % WT_FOLD) == WT_FOLD - 1 || s == nst - 1;
+      if (first_in_grp && s > 0) { wa.wait(b_accfree, ph_accfree, 1); ph_accfree ^= 1; }
+      wa.wait(&b_afull[b], (ph_afull >> b) & 1u, 2); ph_afull ^= 1u << b;
+      fence_after_sync();
+      if (leader) {
+        const uint32_t eb = op_addr + (uint32_t)(ob * OPF + 2 * UB) * 4u;
+        const uint32_t stg = tbase + STG0 + b * STGW;
+#pragma unroll
+        for (int j = 0; j < WT_ROWS / 8; ++j) {
+          const uint32_t acc = (first_in_grp && j == 0) ? 0u : 1u;
+          for (int n = net_lo; n <= net_hi; ++n) {
+            const uint32_t ebn = eb + (uint32_t)(n * 2 * EBN) * 4u, d2 = tbase + ACC2 + n * 2 * TP;
+            mma_tf32_ts(d2, stg + 64 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e2, acc);                  // h_hi x [e_hi ; e_lo]
+            mma_tf32_ts(d2 + TP, stg + 96 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e, 1u);               // h_lo x e_hi
+          }
+        }
+        mma_commit(&b_opfree[ob]);
+        mma_commit(&b_hfree[b]);
+        if (last_in_grp) mma_commit(b_accfull);
+      }
+      __syncwarp();
+    }
+    if (leader) wa.flush(a.trace, 1, clock64() - tstart);
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ TMA producer: three bulk copies per stage
+    if (lane == 0) {
+      const uint32_t bytes_h = (uint32_t)(WT_ROWS * ncols_h) * 4u;
+      WaitAcc wa; wa.init((a.trace != nullptr && blockIdx.x == 0));
+      const long long tstart = clock64();
+      for (int s = 0; s < nst; ++s) {
+        const int slot = s % NSLOT;
+        if (s >= NSLOT) wa.wait(&b_empty[slot], (uint32_t)((s / NSLOT - 1) & 1), 0, true);
+        const float* src = gblk + (size_t)s * block_floats;
+        float* dst = raw + slot * RAW;
+        mbar_expect_tx(&b_full[slot], bytes_h + (uint32_t)(RAW_U + RAW_E) * 4u);
+        bulk_g2s(dst, src + (size_t)WT_ROWS * 128 * mb, bytes_h, &b_full[slot]);
+        bulk_g2s(dst + RAW_H, src + (size_t)WT_ROWS * H2, (uint32_t)RAW_U * 4u, &b_full[slot]);
+        bulk_g2s(dst + RAW_H + RAW_U, src + (size_t)WT_ROWS * (H2 + K1P8), (uint32_t)RAW_E * 4u, &b_full[slot]);
+      }
+      wa.flush(a.trace, 4, clock64() - tstart);
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------------ converters (lanes = rows)
     const int cw = warp - 2;
-    const int ncg_u = K1P8 >> 2;
-    constexpr int NCGE = (2 * TP) / 4;                                      // column groups of delta2 (both nets)
+    constexpr int NCGU = K1P8 / 4, NCGE = (2 * TP) / 4, NUW = (NCGU + 1) / 2, NEW = NCGE / 2;
     const int cg_u0 = H2 >> 2, cg_e0 = (H2 + K1P8) >> 2;                  // global column-group index (the slot swizzle uses it)
-    float db2[NCGE / 2][4];
+    float db2[NEW][4];
 #pragma unroll
-    for (int i = 0; i < NCGE / 2; ++i) db2[i][0] = db2[i][1] = db2[i][2] = db2[i][3] = 0.0f;
+    for (int i = 0; i < NEW; ++i) db2[i][0] = db2[i][1] = db2[i][2] = db2[i][3] = 0.0f;
     const int r = lane;
     const int koff = (r >> 2) * WT_KG + (r & 3);                           // K-major-over-rows: K-group, position in group
     uint32_t ph_full = 0, ph_free = 0;
+    WaitAcc wa; wa.init((a.trace != nullptr && blockIdx.x == 0) && warp == 2);
+    const long long tstart = clock64();
     for (int s = 0; s < nst; ++s) {
       const int slot = s % NSLOT, ob = s % NOP;
-      mbar_wait(&b_full[slot], (ph_full >> slot) & 1u); ph_full ^= 1u << slot;
-      if (s >= NOP) { mbar_wait(&b_opfree[ob], (ph_free >> ob) & 1u); ph_free ^= 1u << ob; }      // the MMAs that read this buffer are done
-      const float* R = raw + slot * raw_floats;
-      float* ub_hi = op + ob * OPF;
-      float* ub_lo = ub_hi + UB;
-      float* eb = ub_lo + UB;
-      float* dk_hi = eb + 4 * EBN;
-      float* dk_lo = dk_hi + DK;
-      for (int cg = cw; cg < ncg_u; cg += 2) {
-        const float4 v = *reinterpret_cast<const float4*>(R + raw_h + cg * 128 + ((r ^ ((cg_u0 + cg) & 7)) << 2));
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+      wa.wait(&b_full[slot], (ph_full >> slot) & 1u, 0); ph_full ^= 1u << slot;
+      const float* R = raw + slot * RAW;
+      // all of this warp's column groups are loaded before the first store (independent loads in flight)
+      float4 vu[NUW], ve[NEW];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int n = 4 * cg + q, o = (n >> 3) * WT_NG + (n & 7) * 4 + koff;
-          ub_hi[o] = vv[q];
-          ub_lo[o] = lo_part(vv[q]);
+      for (int i = 0; i < NUW; ++i) {
+        const int cg = cw + 2 * i;
+        vu[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cg < NCGU) vu[i] = *reinterpret_cast<const float4*>(R + RAW_H + cg * 128 + ((r ^ ((cg_u0 + cg) & 7)) << 2));
+      }
+#pragma unroll
+      for (int i = 0; i < NEW; ++i) {
+        const int cg = cw + 2 * i;
+        ve[i] = *reinterpret_cast<const float4*>(R + RAW_H + RAW_U + cg * 128 + ((r ^ ((cg_e0 + cg) & 7)) << 2));
+      }
+      if (s >= NOP) { wa.wait(&b_opfree[ob], (ph_free >> ob) & 1u, 1); ph_free ^= 1u << ob; }      // the MMAs that read this buffer are done
+      float* ub_hi = op + ob * OPF;
+      float* eb = ub_hi + 2 * UB;
+      float* dk_hi = eb + 4 * EBN;
+#pragma unroll
+      for (int i = 0; i < NUW; ++i) {
+        const int cg = cw + 2 * i;
+        if (cg < NCGU) {
+          const float vv[4] = {vu[i].x, vu[i].y, vu[i].z, vu[i].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = 4 * cg + q, o = (n >> 3) * WT_NG + (n & 7) * 4 + koff;
+            ub_hi[o] = vv[q];
+            ub_hi[UB + o] = lo_part(vv[q]);
+          }
         }
       }
 #pragma unroll
-      for (int i = 0; i < NCGE / 2; ++i) {
+      for (int i = 0; i < NEW; ++i) {
         const int cg = cw + 2 * i;
-        const float4 v = *reinterpret_cast<const float4*>(R + raw_h + raw_u + cg * 128 + ((r ^ ((cg_e0 + cg) & 7)) << 2));
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const float vv[4] = {ve[i].x, ve[i].y, ve[i].z, ve[i].w};
         const int net = (4 * cg) / TP;
         float* en_hi = eb + net * 2 * EBN;
 #pragma unroll
@@ -229,19 +331,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
         }
         // operand of the dh product: [N = rows, K = 2TP], core matrices of 8 rows x 4 columns
         const int o2 = (r >> 3) * (2 * TP / 4) * 32 + cg * 32 + (r & 7) * 4;
-        *reinterpret_cast<float4*>(dk_hi + o2) = v;
-        *reinterpret_cast<float4*>(dk_lo + o2) = make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
+        *reinterpret_cast<float4*>(dk_hi + o2) = ve[i];
+        *reinterpret_cast<float4*>(dk_hi + DK + o2) = make_float4(lo_part(vv[0]), lo_part(vv[1]), lo_part(vv[2]), lo_part(vv[3]));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> tensor-core reads
       mbar_arrive(&b_conv[ob]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_empty[slot]);
     }
+    if (lane == 0) wa.flush(a.trace, 2, clock64() - tstart);
     // db2[e] = sum over this CTA's rows of delta2[:, e]; the CTA of lane block 0 contributes it
     if (mb == 0 && nst > 0) {
       const RnvpWgradLayer& lw = a.layers[layer];
 #pragma unroll
-      for (int i = 0; i < NCGE / 2; ++i) {
+      for (int i = 0; i < NEW; ++i) {
         const int cg = cw + 2 * i;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -282,7 +385,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
       tmem_wait_st();
       fence_before_sync();
     }
-    asm volatile("bar.sync 1, 288;" ::: "memory");               // owners (256) + issuer warp (32): the image is in place
+    asm volatile("bar.sync 1, 288;" ::: "memory");               // owners (256) + issuer A (32): the image is in place
     // half 0 keeps the running sums of dW1 (this unit's row), half 1 those of dW2 (this unit's column, own net)
     constexpr int NS = NU > TP ? NU : TP;
     float sum[NS];
@@ -291,17 +394,29 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
     float db1 = 0.0f;
     const bool is_tanh = a.act == 1;
     const int hcg = m >> 2, hq = m & 3;
-    uint32_t ph_full = 0, ph_dh = 0, ph_acc = 0;
-    for (int s = 0; s < nst; ++s) {
-      const int slot = s % NSLOT, b = s % NBUF;
-      mbar_wait(&b_full[slot], (ph_full >> slot) & 1u); ph_full ^= 1u << slot;
-      const float* Rh = raw + slot * raw_floats + hcg * 128 + hq;
-      uint32_t hh[16];
+    uint32_t ph_full = 0, ph_dh = 0, ph_hfree = 0, ph_acc = 0;
+    WaitAcc wa; wa.init((a.trace != nullptr && blockIdx.x == 0) && warp == 4);
+    const long long tstart = clock64();
+    uint32_t hh[16];
+    // h of stage s (this unit, this thread's 16 rows) from the raw ring; releases the slot for this warp
+    auto load_h = [&](int s) {
+      const int slot = s % NSLOT;
+      wa.wait(&b_full[slot], (ph_full >> slot) & 1u, 0); ph_full ^= 1u << slot;
+      const float* Rh = raw + slot * RAW + hcg * 128 + hq;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) hh[r] = valid ? __float_as_uint(Rh[((16 * half + r) ^ (hcg & 7)) << 2]) : 0u;
+      for (int r = 0; r < 16; ++r) hh[r] = __float_as_uint(Rh[((16 * half + r) ^ (hcg & 7)) << 2]);
+      if (!valid) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) hh[r] = 0u;
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&b_empty[slot]);
-      mbar_wait(&b_dh[b], (ph_dh >> b) & 1u); ph_dh ^= 1u << b;
+    };
+    if (nst > 0) load_h(0);
+    for (int s = 0; s < nst; ++s) {
+      const int b = s % NBUF;
+      wa.wait(&b_dh[b], (ph_dh >> b) & 1u, 1); ph_dh ^= 1u << b;
+      if (s >= NBUF) { wa.wait(&b_hfree[b], (ph_hfree >> b) & 1u, 2); ph_hfree ^= 1u << b; }    // issuer B is done with this buffer
       fence_after_sync();
       const uint32_t stg = trow + STG0 + b * STGW + 16 * half;
       uint32_t dh[16], lo[16];
@@ -325,9 +440,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
       tmem_wait_st();
       fence_before_sync();
       mbar_arrive(&b_afull[b]);
+      if (s + 1 < nst) load_h(s + 1);             // overlaps with the issuers' work on this stage
       // drain a finished accumulator chain into the fp32 register sums
       if ((s % WT_FOLD) == WT_FOLD - 1 || s == nst - 1) {
-        mbar_wait(b_accfull, ph_acc); ph_acc ^= 1;
+        wa.wait(b_accfull, ph_acc, 3); ph_acc ^= 1;
         fence_after_sync();
         if (half == 0) {
 #pragma unroll
@@ -355,6 +471,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
         mbar_arrive(b_accfree);
       }
     }
+    if (lane == 0) wa.flush(a.trace, 3, clock64() - tstart);
     // ---- flush: this unit's row of dW1 (half 0), its column of dW2 (half 1), db1 (both halves' partial sums)
     if (nst > 0 && valid) {
       if (half == 0) {
@@ -375,12 +492,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tbase, 512);
+  if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
-template <int NU, int TP, int NBUF, int NOP, int NSLOT>
+template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT>
 cudaError_t launch_tc(const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
-  auto k = rnvp_wgrad_tc_kernel<NU, TP, NBUF, NOP, NSLOT>;
+  if (a.K1P8 != K1P8) return cudaErrorInvalidValue;
+  auto k = rnvp_wgrad_tc_kernel<NU, K1P8, TP, NBUF, NOP, NSLOT>;
   const size_t smem = rnvp_wgrad_tc_smem_bytes(NU, TP, NBUF, NOP, NSLOT, a.K1P8);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -393,12 +511,20 @@ cudaError_t launch_tc(const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
 size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, int K1P8) {
   const size_t raw = (size_t)WT_ROWS * (128 + K1P8 + 2 * TP);
   const size_t opf = 2 * (size_t)(NU / 8) * WT_NG + 4 * (size_t)(TP / 8) * WT_NG + 2 * (size_t)WT_ROWS * 2 * TP;
-  return (NSLOT * raw + NOP * opf) * 4 + 8 * (2 * NSLOT + 2 * NOP + 2 * NBUF + 2) + 64;
+  return (NSLOT * raw + NOP * opf) * 4 + 8 * (2 * NSLOT + 2 * NOP + 3 * NBUF + 2) + 64;
 }
 
 // D = 32 flows: NU 32, TP 16.  D = 64 flows: NU 48, TP 32 (one staging buffer: TMEM columns)
 cudaError_t rnvp_launch_wgrad_tc(int NU, int TP, const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
-  if (NU == 32 && TP == 16) return launch_tc<32, 16, 2, 4, 4>(a, grid, st);
-  if (NU == 48 && TP == 32) return launch_tc<48, 32, 1, 3, 4>(a, grid, st);
+  if (NU == 32 && TP == 16 && a.K1P8 == 24) {
+    const char* v = getenv("RNVP_WG_VARIANT");     // development knob: ring-depth experiments
+    const int var = v ? atoi(v) : 0;
+    if (var == 1) return launch_tc<32, 24, 16, 2, 2, 7>(a, grid, st);
+    if (var == 2) return launch_tc<32, 24, 16, 2, 3, 6>(a, grid, st);
+    if (var == 3) return launch_tc<32, 24, 16, 2, 2, 4>(a, grid, st);
+    return launch_tc<32, 24, 16, 2, 4, 4>(a, grid, st);
+  }
+  if (NU == 32 && TP == 16 && a.K1P8 == 16) return launch_tc<32, 16, 16, 2, 4, 4>(a, grid, st);
+  if (NU == 48 && TP == 32 && a.K1P8 == 48) return launch_tc<48, 48, 32, 1, 3, 4>(a, grid, st);
   return cudaErrorInvalidValue;
 }
