@@ -33,6 +33,7 @@ size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats, int w1t_floats);
 cudaError_t rnvp_launch_wgrad(int NT1, int NT2, const RnvpWgradArgs& a, int grid, size_t smem, cudaStream_t st);
 size_t rnvp_wgrad_smem_bytes(int rec, int bw);
 cudaError_t rnvp_launch_wgrad_tc(int NU, int TP, const RnvpWgradTcArgs& a, int grid, cudaStream_t st);
+cudaError_t rnvp_launch_wide(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, cudaStream_t st);
 cudaError_t rnvp_launch_mma_selftest(const float* A, const float* B, float* D, int N, int K, int passes, cudaStream_t st);
 
 namespace {
@@ -261,6 +262,8 @@ long long* g_mma_trace = nullptr;   // development aid, see rnvp_debug_set_trace
 bool use_mma(const rnvp_desc* d) { return d->mma_ok && d->path != 1; }
 // fit step entirely on the tensor-core path (tcgen05 forward + backward sweeps, mma.sync weight-gradient sweep)
 bool use_mma_bwd(const rnvp_desc* d) { return use_mma(d) && d->m_wt_floats > 0; }
+// forward sweep of a fit step on the tensor cores (stash for the FP32 backward sweep): resident-image kernels only
+bool use_mma_fwd_stash(const rnvp_desc* d) { return use_mma(d) && !d->m_stream; }
 // record stride of the activation records exchanged between the backward sweep and the weight-gradient sweep
 int wgrad_rec_floats(const rnvp_desc* d) {
   const int K1P = (d->mDH + d->Cd + 7) & ~7;
@@ -285,6 +288,16 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.wt_floats = records ? d->m_wt_floats : 0;
   a.trace = g_mma_trace;
   a.seed = seed; a.row_offset = row_offset;
+  if (d->m_stream) {
+    if (mode == 2) return fail(RNVP_ESHAPE, "streamed tcgen05 kernels have no fit sweep");
+    const long long tiles = (N + 127) / 128;
+    if (tiles > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
+    a.n_pairs = (int)tiles;                      // rnvp_wide.cu walks single 128-row tiles
+    a.wt_floats = 0;
+    cudaError_t e = rnvp_launch_wide(d->mDH, d->act, mode, a, (int)std::min<long long>(tiles, d->num_sms), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tcgen05 streamed kernel launch");
+    return 0;
+  }
   const long long pairs = (N + 255) / 256;
   if (pairs > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
   a.n_pairs = (int)pairs;
@@ -412,7 +425,7 @@ int64_t rnvp_workspace_bytes(const rnvp_desc* dc, int64_t N) {
     const int64_t n = std::max<int64_t>(N, 1), npad = (n + 255) / 256 * 256;
     return (npad * d->L * 2 * d->mDH + (int64_t)d->L * npad * wgrad_rec_floats(d)) * 4;
   }
-  if (use_mma(d)) return std::max<int64_t>(N, 1) * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
+  if (use_mma_fwd_stash(d)) return std::max<int64_t>(N, 1) * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
   Program* p = nullptr;
   if (get_program(d, 2, 0, d->L, &p)) return -1;
   return (int64_t)p->stash_per_cta * 4 * d->num_sms * p->occupancy;
@@ -444,7 +457,7 @@ int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_byte
   if (tile_rows) *tile_rows = 8 * p->TR;
   if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
   if (n_ops) *n_ops = p->n_ops;
-  if (kernel_family) *kernel_family = use_mma(d) ? 2 : (((mode < 2 && d->small_ok) || (mode == 2 && use_small_fit(d))) ? 1 : 0);
+  if (kernel_family) *kernel_family = (mode >= 2 ? use_mma_fwd_stash(d) : use_mma(d)) ? 2 : (((mode < 2 && d->small_ok) || (mode == 2 && use_small_fit(d))) ? 1 : 0);
   return 0;
 }
 
@@ -553,7 +566,7 @@ int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, 
     if (rc) return rc;
     return rnvp_wgrad_sweep(d, d_packed, npad, records, d_gpacked, stream);
   }
-  if (use_mma(d) && N > 0) {
+  if (use_mma_fwd_stash(d) && N > 0) {
     // forward sweep on the tensor cores (z, per-layer x_T and s to the workspace), backward sweep on the FP32 tile kernel
     const int64_t need = (int64_t)N * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
     if (!d_workspace || workspace_bytes < need)

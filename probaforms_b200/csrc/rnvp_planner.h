@@ -53,6 +53,7 @@ struct FlowGeom {
   bool mma_ok = false;
   int mDH = 0, mCDMAX = 0, mCU = 0, mK1P = 0, mNTP = 0;
   bool m_netseq = false;
+  bool m_stream = false;   // weight images streamed per chunk step (rnvp_wide.cu) instead of resident per layer
   int m_w1_floats = 0, m_w2_floats = 0, m_b2_floats = 0, m_layer_floats = 0;
   int m_wt_floats = 0;   // transposed images for the backward sweep (W2T then W1T, m_wt_floats each), 0 if not built
   int64_t mma_off = 0, mma_floats = 0;
@@ -114,15 +115,21 @@ inline void build_layout(FlowGeom* d) {
   d->packed_gather = d->packed;
   // tcgen05 layout
   d->mma_ok = false;
-  if (nh == 1 && D % 2 == 0 && (D / 2 == 16 || D / 2 == 32)) {
+  d->m_stream = false;
+  if (nh == 1 && D % 2 == 0 && (D / 2 == 16 || D / 2 == 32 || D / 2 == 64)) {
     const int DH = D / 2, H = d->hidden[0];
-    const int CDMAX = DH == 16 ? 8 : 16, CU = 32;
-    const bool netseq = DH == 32;                              // nn_t chunks before nn_s chunks (rnvp_mma.cu)
+    const int CDMAX = DH == 16 ? 8 : (DH == 32 ? 16 : 32), CU = 32;
+    const bool netseq = DH >= 32;                              // nn_t chunks before nn_s chunks (rnvp_mma.cu / rnvp_wide.cu)
     const int K1P = (DH + Cd + 1 + 7) & ~7, NTP = (DH + 15) & ~15;
     const int tile_cols = netseq ? 2 * K1P + 2 * CU + 2 * NTP : 2 * K1P + 4 * CU + 4 * NTP;
     const int64_t w1 = (int64_t)4 * H * K1P, w2 = (int64_t)4 * NTP * H;
-    if (Cd <= CDMAX && H % CU == 0 && H >= CU && tile_cols <= 256 && (w1 + w2 + 32 * NTP) * 4 + 2048 <= d->max_smem) {
+    // whole-layer images resident in shared memory (rnvp_mma.cu), or streamed per chunk step (rnvp_wide.cu: D = 64 / 128
+    // flows whose images are too large, e.g. BASELINE configs[4] with 1.36 MB per layer)
+    const bool resident = DH <= 32 && tile_cols <= 256 && (w1 + w2 + 32 * NTP) * 4 + 2048 <= d->max_smem;
+    const bool streamed = !resident && DH >= 32;
+    if (Cd <= CDMAX && H % CU == 0 && H >= CU && (resident || streamed)) {
       d->mma_ok = true;
+      d->m_stream = streamed;
       d->mDH = DH; d->mCDMAX = CDMAX; d->mCU = CU; d->mK1P = K1P; d->mNTP = NTP; d->m_netseq = netseq;
       d->m_b2_floats = 32 * NTP;                               // 2 nets x [hi | lo] x [NTP x 8]
       d->m_w1_floats = (int)w1; d->m_w2_floats = (int)w2 + d->m_b2_floats;  // b2 images ride with the W2 copy

@@ -1,0 +1,356 @@
+// tcgen05 path for WIDE flows (BASELINE configs[4]: D = 128, Cd = 32, H = 512; also D = 64 flows whose weight images do
+// not fit shared memory): fused forward (log-density) and inverse (sampling) passes with the conditioner weights STREAMED.
+//
+// rnvp_mma.cu keeps the TF32 hi/lo images of a whole coupling layer in shared memory and walks two 128-row tiles per
+// CTA.  Here a layer's images are 1.36 MB (c5), a row is 128 + 32 floats and the hidden layer has 2 x 512 units, so:
+//   * one persistent CTA per SM owns ONE 128-row tile at a time; TMEM holds u = [x_K, c, 1] (hi/lo, 2 x K1PMAX columns), a
+//     double-buffered GEMM1 accumulator chunk (D1 / A_hi in place, A_lo; 2 x 2 x CU columns) and the GEMM2 accumulators
+//     [D2 | C2] (2 x NTP columns) -- 464 of 512 columns for c5;
+//   * the hidden units are processed in chunk steps of CU = 32 units, nn_t's chunks first (t parked in registers), then
+//     nn_s's; per chunk step the TMA producer (warp 0) streams the W1 chunk image [hi | lo], the W2 chunk image
+//     [hi | lo] (and, at the first chunk of a net, its b2 image) from the L2-resident packed buffer into a 4-stage ring
+//     (43 KB per stage for c5: every SM reads the same 1.36 MB per tile-layer -- 29 B/cycle/SM, under the L2 cap);
+//   * the MMA issuer (warp 1, one elected lane) runs GEMM1 of chunk step cc+1 BEFORE it waits for the activations of chunk
+//     step cc, so the tensor core works on the next chunk while the epilogue warps turn the current one into tanh(.);
+//     error-compensated TF32 split as in rnvp_mma.cu (corrections first in GEMM1, merged A_hi x [B_hi ; B_lo] in GEMM2);
+//   * warps 4-11 are the epilogue: TWO THREADS PER ROW (a thread cannot hold a 128-D row): thread (row, half) owns half of
+//     the transformed and half of the conditioning features, writes its half of u, converts its 16 columns of every D1
+//     chunk and applies the coupling to its 32 features; the two partial log-dets / squared norms meet in shared memory.
+// Reference semantics: RealNVPLayer.f / .g (realnvp.py:73-129) looped as in nflow.py:109-115 / 142-143.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tc05.cuh"
+#include "rnvp_mma.h"
+#include "rnvp_philox.cuh"
+
+namespace {
+using namespace tc05;
+
+constexpr int WD_THREADS = 384;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle, warps 4-11 epilogue
+constexpr int WD_STAGES = 4;          // weight ring depth (chunk steps in flight)
+
+template <int ACT>
+__device__ __forceinline__ float act_wide(float v) {
+  if (ACT == 1) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+  }
+  return fmaxf(v, 0.0f);
+}
+// exp(x) on the MUFU with the argument's rounding error compensated (see rnvp_mma.cu exp_mma)
+__device__ __forceinline__ float exp_wide(float x) {
+  const float t = x * 1.4426950216293335f;
+  const float r = fmaf(x, 1.9259629911266175e-8f, fmaf(x, 1.4426950216293335f, -t));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return fmaf(e, r * 0.6931471805599453f, e);
+}
+
+// barrier indices: ring full / empty first, then the tile hand-offs
+enum { WB_WF = 0, WB_WE = WD_STAGES, WB_UF = 2 * WD_STAGES, WB_D1F0, WB_D1F1, WB_AF0, WB_AF1, WB_D2F, WB_COUNT };
+
+template <int DH, int CDMAX, int CU, int ACT, int MODE>
+__global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_constant__ RnvpMmaArgs a) {
+  constexpr int K1PMAX = (DH + CDMAX + 1 + 7) & ~7;
+  constexpr int NTP = (DH + 15) & ~15;
+  constexpr int HALF = DH / 2;                         // features of each parity class owned by one thread of a row pair
+  // TMEM columns
+  constexpr int U_HI = 0, U_LO = K1PMAX, D1B = 2 * K1PMAX;               // D1 ring: buffer b at D1B + b*2*CU: [D1/A_hi | A_lo]
+  constexpr int D2C = D1B + 4 * CU, C2C = D2C + NTP, TCOLS = C2C + NTP;
+  static_assert(TCOLS <= 512, "TMEM budget");
+  static_assert(DH % 16 == 0 && (K1PMAX - DH) % 8 == 0 && CU == 32, "layout assumptions");
+
+  extern __shared__ __align__(128) float sm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.H, Cd = a.Cd, D = 2 * DH;
+  const int NC = H / CU, NCS = 2 * NC;                  // chunk steps per layer: nn_t chunks, then nn_s chunks
+  const int K1P = (DH + Cd + 1 + 7) & ~7;
+  const int nL = a.l1 - a.l0;
+  const int w1c = 2 * CU * K1P;                         // floats of one W1 chunk image [hi | lo]
+  constexpr int W2C = 2 * NTP * CU, B2C = 2 * NTP * 8;  // W2 chunk image [hi | lo]; b2 image of one net [hi | lo]
+  const int stage_floats = ((2 * CU * K1PMAX + W2C + B2C) + 31) & ~31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + WD_STAGES * stage_floats);
+  float* xch = reinterpret_cast<float*>(bars + WB_COUNT);                 // [128][2]: partial (logdet, |z|^2) of the second half-thread
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xch + 256);
+
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (tid == 0) {
+    for (int s = 0; s < WD_STAGES; ++s) { mbar_init(&bars[WB_WF + s], 1); mbar_init(&bars[WB_WE + s], 1); }
+    mbar_init(&bars[WB_UF], 256);
+    mbar_init(&bars[WB_D1F0], 1); mbar_init(&bars[WB_D1F1], 1);
+    mbar_init(&bars[WB_AF0], 256); mbar_init(&bars[WB_AF1], 256);
+    mbar_init(&bars[WB_D2F], 1);
+    mbar_fence_init();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const int my_tiles = (a.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // n_pairs = number of 128-row tiles here
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: one ring stage per chunk step
+    if (lane == 0) {
+      long long step = 0;
+      const uint32_t w1c_bytes = (uint32_t)w1c * 4u, w2c_bytes = (uint32_t)W2C * 4u, b2_bytes = (uint32_t)B2C * 4u;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int li = 0; li < nL; ++li) {
+          const int i = MODE == 1 ? a.l1 - 1 - li : a.l0 + li;
+          const float* L0 = a.wimg + (size_t)i * a.layer_floats;
+          const float* W2 = L0 + a.w1_floats;
+          const float* B2 = W2 + (size_t)4 * NTP * H;
+          for (int cc = 0; cc < NCS; ++cc, ++step) {
+            const int st = (int)(step % WD_STAGES);
+            if (step >= WD_STAGES) mbar_wait_relaxed(&bars[WB_WE + st], (uint32_t)((step / WD_STAGES - 1) & 1));
+            const int net = cc >= NC ? 1 : 0, c = cc - net * NC;
+            float* dst = sm + (size_t)st * stage_floats;
+            const bool with_b2 = c == 0;
+            mbar_expect_tx(&bars[WB_WF + st], w1c_bytes + w2c_bytes + (with_b2 ? b2_bytes : 0u));
+            bulk_g2s(dst, L0 + (size_t)cc * w1c, w1c_bytes, &bars[WB_WF + st]);
+            bulk_g2s(dst + 2 * CU * K1PMAX, W2 + (size_t)(c * 2 + net) * W2C, w2c_bytes, &bars[WB_WF + st]);
+            if (with_b2) bulk_g2s(dst + 2 * CU * K1PMAX + W2C, B2 + (size_t)net * B2C, b2_bytes, &bars[WB_WF + st]);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    const uint32_t idesc1 = idesc_tf32(128, CU), idesc2 = idesc_tf32(128, NTP), idesc2m = idesc_tf32(128, 2 * NTP);
+    const uint32_t lbo = (128u >> 4) << 16;
+    const uint32_t hi1 = ((uint32_t)(K1P >> 2) * 128u >> 4) | (1u << 14);       // SBO of the W1 chunk image, descriptor version 1
+    const uint32_t hi2 = ((uint32_t)(CU >> 2) * 128u >> 4) | (1u << 14);        // W2 chunk image: [NTP (x2) rows x CU]
+    const uint32_t hib = (256u >> 4) | (1u << 14);                              // b2 image: K = 8
+    const uint32_t chunk1 = (uint32_t)(CU * K1P) * 4u >> 4;                     // one hi (or lo) W1 chunk, 16 B units
+    const int nk1 = K1P >> 3;
+    const int k_one = (DH + Cd) & ~7;                                           // u slice holding the constant one
+    auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    const uint32_t sm_lo = ((smem_u32(sm) & 0x3FFFFu) >> 4) | lbo;
+    const uint32_t stage16 = (uint32_t)stage_floats * 4u >> 4;
+    // GEMM1 of a chunk step into D1 buffer `buf`: [u_lo W1_hi + u_hi W1_lo] + u_hi W1_hi (corrections first)
+    auto gemm1 = [&](int st, int buf) {
+      const uint32_t bh = sm_lo + (uint32_t)st * stage16, bl = bh + chunk1;
+      const uint32_t d = tbase + D1B + buf * 2 * CU;
+#pragma unroll
+      for (int j = 0; j < K1PMAX / 8; ++j)
+        if (j < nk1) mma_tf32_ts(d, tbase + U_LO + 8 * j, desc(bh + 16u * j, hi1), idesc1, j ? 1u : 0u);
+#pragma unroll
+      for (int j = 0; j < K1PMAX / 8; ++j)
+        if (j < nk1) mma_tf32_ts(d, tbase + U_HI + 8 * j, desc(bl + 16u * j, hi1), idesc1, 1u);
+#pragma unroll
+      for (int j = 0; j < K1PMAX / 8; ++j)
+        if (j < nk1) mma_tf32_ts(d, tbase + U_HI + 8 * j, desc(bh + 16u * j, hi1), idesc1, 1u);
+    };
+    // GEMM2 of chunk c of a net: [D2 | C2] (+)= A_hi x [W2_hi ; W2_lo]  (one MMA of N = 2 NTP), C2 += A_lo x W2_hi; the first
+    // chunk seeds [D2 | C2] with 1 x [b2_hi ; b2_lo]
+    auto gemm2 = [&](int st, int buf, int c) {
+      const uint32_t w2 = sm_lo + (uint32_t)st * stage16 + ((uint32_t)(2 * CU * K1PMAX) * 4u >> 4);
+      const uint32_t b2 = w2 + ((uint32_t)W2C * 4u >> 4);
+      const uint32_t ah = tbase + D1B + buf * 2 * CU, al = ah + CU;
+      if (c == 0) mma_tf32_ts(tbase + D2C, tbase + U_HI + k_one, desc(b2, hib), idesc2m, 0u);
+#pragma unroll
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(tbase + C2C, al + 8 * j, desc(w2 + 16u * j, hi2), idesc2, 1u);
+#pragma unroll
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(tbase + D2C, ah + 8 * j, desc(w2 + 16u * j, hi2), idesc2m, 1u);
+    };
+    uint32_t ph_u = 0, ph_a = 0, ph_w = 0;              // ph_a / ph_w: one bit per buffer / stage
+    long long step = 0;
+    for (int it = 0; it < my_tiles; ++it)
+      for (int li = 0; li < nL; ++li) {
+        mbar_wait(&bars[WB_UF], ph_u); ph_u ^= 1;
+        {
+          const int st = (int)(step % WD_STAGES);
+          mbar_wait(&bars[WB_WF + st], (ph_w >> st) & 1u); ph_w ^= 1u << st;
+          fence_after_sync();
+          if (leader) { gemm1(st, 0); mma_commit(&bars[WB_D1F0]); }
+          __syncwarp();
+        }
+        for (int cc = 0; cc < NCS; ++cc, ++step) {
+          const int st = (int)(step % WD_STAGES), buf = cc & 1;
+          if (cc + 1 < NCS) {                 // next chunk's GEMM1 first: the tensor core stays busy during this chunk's epilogue
+            const int st1 = (int)((step + 1) % WD_STAGES);
+            mbar_wait(&bars[WB_WF + st1], (ph_w >> st1) & 1u); ph_w ^= 1u << st1;
+            fence_after_sync();
+            if (leader) { gemm1(st1, buf ^ 1); mma_commit(&bars[WB_D1F0 + (buf ^ 1)]); }
+            __syncwarp();
+          }
+          mbar_wait(&bars[WB_AF0 + buf], (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          fence_after_sync();
+          if (leader) {
+            const int net = cc >= NC ? 1 : 0;
+            gemm2(st, buf, cc - net * NC);
+            mma_commit(&bars[WB_WE + st]);                       // both GEMMs that read this ring stage are issued
+            if (cc + 1 == NC || cc + 1 == NCS) mma_commit(&bars[WB_D2F]);
+          }
+          __syncwarp();
+        }
+      }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: two threads per row
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const uint32_t trow = tbase + ((uint32_t)(quarter * 32) << 16);
+    const int rin = quarter * 32 + lane;                 // row inside the tile
+    uint32_t ph_d1 = 0, ph_d2 = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      const long long row = tile * 128 + rin;
+      const bool valid = row < a.N;
+      const long long src = valid ? (a.idx ? a.idx[row] : row) : 0;
+      // this thread's features: [half*DH, (half+1)*DH) of the row = HALF even-indexed (xa) and HALF odd-indexed (xb) ones
+      float xa[HALF], xb[HALF], ld = 0.0f;
+#pragma unroll
+      for (int m = 0; m < HALF / 2; ++m) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 1 && a.X == nullptr) { if (valid) v = rnvp_rng::normal4(a.seed, a.row_offset + row, half * (DH / 4) + m); }
+        else if (valid) v = __ldg(reinterpret_cast<const float4*>(a.X + src * D + half * DH) + m);
+        xa[2 * m] = v.x; xb[2 * m] = v.y; xa[2 * m + 1] = v.z; xb[2 * m + 1] = v.w;
+      }
+      // static part of u: [c | 1 | 0...] at columns DH.. of U_HI / U_LO, written once per tile; the 8-column pieces are
+      // shared out between the two threads of the row
+#pragma unroll
+      for (int e0 = 0; e0 < K1PMAX - DH; e0 += 8) {
+        if (((e0 >> 3) & 1) == half) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = e0 + j;
+            float v = 0.0f;
+            if (k < Cd && valid) v = __ldg(a.C + src * Cd + k);
+            if (k == Cd) v = 1.0f;
+            split_tf32(v, hi[j], lo[j]);
+          }
+          tmem_st_x8(trow + U_HI + DH + e0, hi);
+          tmem_st_x8(trow + U_LO + DH + e0, lo);
+        }
+      }
+
+      auto layer = [&](float (&xT)[HALF], float (&xK)[HALF]) {
+        // ---- this thread's half of the conditioning features -> u (hi / lo) in TMEM
+#pragma unroll
+        for (int e0 = 0; e0 < HALF; e0 += 8) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_tf32(xK[e0 + j], hi[j], lo[j]);
+          tmem_st_x8(trow + U_HI + half * HALF + e0, hi);
+          tmem_st_x8(trow + U_LO + half * HALF + e0, lo);
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        mbar_arrive(&bars[WB_UF]);
+        float tpark[HALF];
+        for (int cc = 0; cc < NCS; ++cc) {
+          const int buf = cc & 1;
+          mbar_wait(&bars[WB_D1F0 + buf], (ph_d1 >> buf) & 1u); ph_d1 ^= 1u << buf;
+          fence_after_sync();
+          {
+            // this thread's 16 columns of the chunk: D1 -> act -> A_hi (in place), A_lo
+            const uint32_t d1 = trow + D1B + buf * 2 * CU + 16 * half;
+            uint32_t r[16], lo[16];
+            tmem_ld_x16(d1, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_tf32(act_wide<ACT>(__uint_as_float(r[j])), r[j], lo[j]);
+            tmem_st_x16(d1, r);
+            tmem_st_x16(d1 + CU, lo);
+          }
+          tmem_wait_st();
+          fence_before_sync();
+          mbar_arrive(&bars[WB_AF0 + buf]);
+          if (cc + 1 == NC) {                    // nn_t complete: t = D2 + C2 into registers (the nn_s GEMM2 overwrites them)
+            mbar_wait(&bars[WB_D2F], ph_d2); ph_d2 ^= 1;
+            fence_after_sync();
+#pragma unroll
+            for (int e0 = 0; e0 < HALF; e0 += 16) {
+              uint32_t tv[16], tc[16];
+              tmem_ld_x16(trow + D2C + half * HALF + e0, tv);
+              tmem_ld_x16(trow + C2C + half * HALF + e0, tc);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) tpark[e0 + j] = __uint_as_float(tv[j]) + __uint_as_float(tc[j]);
+            }
+            fence_before_sync();                 // ordered before this thread's next a_full arrival, which releases D2 / C2
+          }
+        }
+        // ---- s complete -> coupling on this thread's transformed features
+        mbar_wait(&bars[WB_D2F], ph_d2); ph_d2 ^= 1;
+        fence_after_sync();
+#pragma unroll
+        for (int e0 = 0; e0 < HALF; e0 += 16) {
+          uint32_t sv[16], sc[16];
+          tmem_ld_x16(trow + D2C + half * HALF + e0, sv);
+          tmem_ld_x16(trow + C2C + half * HALF + e0, sc);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s = __uint_as_float(sv[j]) + __uint_as_float(sc[j]);
+            const float t = tpark[e0 + j];
+            if (MODE != 1) { xT[e0 + j] = fmaf(xT[e0 + j], exp_wide(s), t); ld += s; }
+            else xT[e0 + j] = (xT[e0 + j] - t) * exp_wide(-s);
+          }
+        }
+        fence_before_sync();                     // the next layer's first GEMM2 (after the next a_full) overwrites D2 / C2
+      };
+      for (int li = 0; li < nL; ++li) {
+        const int i = MODE != 1 ? a.l0 + li : a.l1 - 1 - li;
+        if ((i & 1) == 0) layer(xa, xb);                 // even layer transforms the even features
+        else layer(xb, xa);
+      }
+
+      if (valid && a.out_x) {
+#pragma unroll
+        for (int m = 0; m < HALF / 2; ++m)
+          reinterpret_cast<float4*>(a.out_x + row * D + half * DH)[m] = make_float4(xa[2 * m], xb[2 * m], xa[2 * m + 1], xb[2 * m + 1]);
+      }
+      if (MODE != 1) {
+        float q = 0.0f;
+#pragma unroll
+        for (int e = 0; e < HALF; ++e) { q = fmaf(xa[e], xa[e], q); q = fmaf(xb[e], xb[e], q); }
+        // the second thread of the row hands its partial sums to the first
+        if (half == 1) { xch[2 * rin] = ld; xch[2 * rin + 1] = q; }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (half == 0 && valid) {
+          const float ldt = ld + xch[2 * rin], qt = q + xch[2 * rin + 1];
+          if (a.out_logdet) a.out_logdet[row] = ldt;
+          if (a.out_logp) a.out_logp[row] = ldt - 0.5f * (D * 1.8378770664093453f + qt);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // xch is reused by the next tile
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+template <int DH, int CDMAX>
+cudaError_t launch_wide_shape(int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+#define RNVP_WIDE_LAUNCH(ACT_, MODE_)                                                                       \
+  {                                                                                                          \
+    auto k = rnvp_wide_kernel<DH, CDMAX, 32, ACT_, MODE_>;                                                   \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    if (e != cudaSuccess) return e;                                                                          \
+    k<<<grid, WD_THREADS, smem, st>>>(a);                                                                    \
+    return cudaGetLastError();                                                                               \
+  }
+  if (act == 1 && mode == 0) RNVP_WIDE_LAUNCH(1, 0)
+  if (act == 1 && mode == 1) RNVP_WIDE_LAUNCH(1, 1)
+  if (act == 2 && mode == 0) RNVP_WIDE_LAUNCH(2, 0)
+  if (act == 2 && mode == 1) RNVP_WIDE_LAUNCH(2, 1)
+#undef RNVP_WIDE_LAUNCH
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+size_t rnvp_wide_smem_bytes(int DH, int CDMAX) {
+  const int K1PMAX = (DH + CDMAX + 1 + 7) & ~7, NTP = (DH + 15) & ~15, CU = 32;
+  const size_t stage = ((size_t)(2 * CU * K1PMAX + 2 * NTP * CU + 2 * NTP * 8) + 31) & ~(size_t)31;
+  return WD_STAGES * stage * 4 + 8 * WB_COUNT + 256 * 4 + 64;
+}
+
+cudaError_t rnvp_launch_wide(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, cudaStream_t st) {
+  if (DH == 64) return launch_wide_shape<64, 32>(act, mode, a, grid, rnvp_wide_smem_bytes(64, 32), st);
+  if (DH == 32) return launch_wide_shape<32, 16>(act, mode, a, grid, rnvp_wide_smem_bytes(32, 16), st);
+  return cudaErrorInvalidValue;
+}
