@@ -13,14 +13,21 @@ batch: tensor-core forward+backward sweep launch, weight-gradient sweep launch, 
 
 value      rows/s, whole job, inputs resident in HBM (a different random batch of a resident
            data set larger than L2 every step -- no L2 flush needed).
-e2e        same metric through the public API ``RealNVP.fit(X, C)`` with pinned HOST arrays:
-           H2D of every step's rows and D2H of the losses inside the timed region.
-roofline   dominant kernel (fused fwd+bwd): algorithmic mask-aware GEMM flops per launch
-           (909,312 / row for c3) / its mean duration from CUDA events inside the
-           timed region, against the FP32-FMA peak 2*128*SMs*max clock (the binding pipe; the
-           path is compute-bound, HBM fraction is reported beside it).
+e2e        same metric through the public API ``RealNVP.fit(X, C)`` from HOST numpy arrays (float64 at
+           N=1): per-step host gather + float32 conversion + H2D of this rank's rows and D2H of the
+           losses inside the timed region (10 M rows per GPU at N=1).
+roofline   the fit kernels (tcgen05 forward+backward sweeps + tcgen05 weight-gradient sweep): EXECUTED
+           tensor flops (3 TF32 passes per algorithmic MAC; 909,312 algorithmic flop / row for c3,
+           SURVEY 8d) / their mean duration from CUDA events inside the timed region, against the
+           measured dense TF32 rate (MEASURED_PEAKS.json bf16 sustained / 2); ``against`` lists the same
+           time versus every other candidate bound (bf16, FP32-FMA equivalent, MUFU, DRAM with the
+           measured bytes of the committed ncu capture, profiles/traffic.json).
 cpu_baseline  the oracle port (same ATen ops as the reference) timed on the host cores on a
            bounded sample, rank 0, N=1 only.
+dp_check   N>1: 5 data-parallel steps == 5 single-process steps on the same rows; sharded sampling ==
+           single-GPU sampling (bit-exact).
+also       configs[0] (c1, with the reference CPU path run in full beside it), [1] (c2), [3] (c4, incl. 125 M
+           rows per GPU = 1 B rows on 8 GPUs) and [4] (c5: tensor-core path and FP32-FMA path side by side).
 """
 import argparse
 import json
@@ -568,17 +575,56 @@ def main():
         f_fwd, f_fit = flops_per_row(D, Cd, L, H)
         kms = float(kern_ms)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        peaks = {}
+        peaks, peak_src = {}, "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s bf16)"
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 peaks = json.load(f)
+            peak_src = "MEASURED_PEAKS.json"
         except Exception:
             pass
         sm_max = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        fp32_peak = 2 * 128 * sms * sm_max * 1e6 / 1e12                   # TFLOP/s, FFMA pipe
-        achieved = per_gpu * f_fit / (kms * 1e-3) / 1e12
+        bf16_sust = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1400.0)
+        tf32_peak = bf16_sust / 2                                         # dense TF32 = half the bf16 rate; sustained: timed inside a long step
+        fp32_peak = 2 * 128 * sms * sm_max * 1e6 / 1e12                   # TFLOP/s, FFMA pipe (the reference's arithmetic type)
+        mufu_peak = 16 * sms * sm_max * 1e6                               # MUFU lanes/s: the tanh (ex2 + rcp) pipe
+        n_tanh = 2 * H * L
+        algo = per_gpu * f_fit / (kms * 1e-3) / 1e12                      # algorithmic (mask-aware) TFLOP/s of the fit kernels
         bytes_row = 4 * (D + Cd) + 8
+        on_tc = eng.fit_on_tensor_cores
+        traffic = load_traffic() if (on_tc and per_gpu == 75776 and args.workload == "c3") else None
+        tr_total = sum(v["dram_bytes"] for v in traffic["kernels"].values()) if traffic else None
+        executed = 3 * algo if on_tc else algo                            # TF32x3: three MMA passes per algorithmic MAC
+        roof = {
+            "bound": "tensor" if on_tc else "fp32_fma",
+            "achieved": executed, "peak": tf32_peak if on_tc else fp32_peak, "unit": "TFLOP/s",
+            "frac": executed / (tf32_peak if on_tc else fp32_peak),
+            "traffic": tr_total,
+            "kernel": ("rnvp_mma_kernel<16,8,32,0,1,2> (tcgen05 TF32x3 forward + backward sweeps) + rnvp_wgrad_tc_kernel "
+                       "(tcgen05 TF32x3 weight-gradient sweep), timed together" if on_tc else
+                       "rnvp_mma_kernel<..,2> (tcgen05 forward sweep) + rnvp_tile_kernel<TR,3> (FP32 backward sweep)"
+                       if eng._bwd_two_kernels else "rnvp_tile_kernel<TR,2> (fused forward+backward)"),
+            "kernel_ms": kms, "kernel_share_of_step": kms / (total_ms / K),
+            "flops_per_row": f_fit, "rows_per_launch": per_gpu,
+            "peak_source": (f"{peak_src}: bf16_tflops_sustained / 2 = dense TF32 (of measured); achieved = EXECUTED tensor flops = 3 x "
+                            "algorithmic (error-compensated TF32 split; operand padding not counted)" if on_tc else
+                            f"FP32-FMA pipe: 2*128 lanes*{sms} SMs*{sm_max:.0f} MHz ({peak_src} sm_max_mhz)"),
+            # the same kernel time against every unit that could bind it (a fraction near 1 would name the bound; none is):
+            "against": {
+                "tensor_tf32_executed": {"achieved_tflops": executed, "peak_tflops": tf32_peak, "frac": executed / tf32_peak},
+                "tensor_bf16_algorithmic": {"achieved_tflops": algo, "peak_tflops": bf16_sust, "frac": algo / bf16_sust,
+                                            "note": "algorithmic flops against the measured bf16 rate: what a bf16 kernel without the split could reach"},
+                "fp32_fma_reference_arithmetic_equivalent": {"achieved_tflops": algo, "peak_tflops": fp32_peak, "frac": algo / fp32_peak,
+                                                             "note": "not a ceiling for a tensor-core kernel; kept for comparison with round 1"},
+                "mufu": {"achieved_per_s": per_gpu * 2 * n_tanh / (kms * 1e-3), "peak_per_s": mufu_peak,
+                         "frac": per_gpu * 2 * n_tanh / (kms * 1e-3) / mufu_peak, "note": "2 MUFU per tanh, forward sweep only"},
+                "dram": ({"measured_bytes_per_step": tr_total, "gbs": tr_total / (kms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                          "frac": tr_total / (kms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_step": per_gpu * bytes_row,
+                          "source": traffic.get("source"), "commit": traffic.get("commit")} if traffic else
+                         {"algorithmic_bytes_per_step": per_gpu * bytes_row, "gbs_algorithmic": per_gpu * bytes_row / (kms * 1e-3) / 1e9,
+                          "peak_gbs": hbm_peak, "note": "no ncu capture committed for this configuration"}),
+            },
+        }
         line = {
             "metric": "RealNVP fit rows/sec (fwd+bwd+Adam)", "value": rows_per_s, "unit": "rows/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
@@ -589,69 +635,60 @@ def main():
                        "l2": f"inputs larger than L2: each step gathers a fresh random batch from a resident "
                              f"{n_res * 4 * (D + Cd) >> 20} MiB data set",
                        "final_loss": final_loss},
-            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak, "traffic": None,
-                         "kernel": ("rnvp_mma_kernel<..,2> (tcgen05 TF32x3 forward + backward sweeps) + rnvp_wgrad_kernel "
-                                    "(mma.sync TF32x3 weight-gradient sweep), timed together"
-                                    if eng.fit_on_tensor_cores else
-                                    "rnvp_mma_kernel<..,2> (tcgen05 forward sweep) + rnvp_tile_kernel<TR,3> (FP32 backward sweep)"
-                                    if eng._bwd_two_kernels else "rnvp_tile_kernel<TR,2> (fused forward+backward)"),
-                         "kernel_ms": kms,
-                         "kernel_share_of_step": kms / (total_ms / K),
-                         "flops_per_row": f_fit, "rows_per_launch": per_gpu,
-                         "peak_source": f"FP32-FMA pipe: 2*128 lanes*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz) -- "
-                                        "the roofline of the reference's arithmetic type; the TF32x3 tensor-core kernels spend 3 "
-                                        "MMA flops per algorithmic flop and are bound by tcgen05.mma issue + the tanh epilogue (DESIGN.md 4)",
-                         "hbm_gbs": per_gpu * bytes_row / (kms * 1e-3) / 1e9,
-                         "hbm_frac_of_measured": per_gpu * bytes_row / (kms * 1e-3) / 1e9 / hbm_peak},
-            "gpu_launches": launches, "clocks": clocks,
+            "roofline": roof, "gpu_launches": launches, "clocks": clocks,
         }
-        bf16_sust = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1346.6)
-        if eng.fit_on_tensor_cores:
-            # transparency: what the tensor pipes actually execute (3 TF32 MMA passes per algorithmic MAC, operand padding
-            # not counted) against the dense TF32 rate (half the measured bf16 rate) -- they are far from saturated; and
-            # the DRAM bytes of one step from the committed ncu capture of this command's kernels (activation records)
-            line["roofline"]["tensor_pipe"] = {
-                "executed_tf32_tflops": 3 * achieved, "peak_tf32_tflops": bf16_sust / 2,
-                "frac": 3 * achieved / (bf16_sust / 2),
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)"}
-            if per_gpu == 75776 and args.workload == "c3":
-                line["roofline"]["traffic"] = 4.52e9
-                line["roofline"]["traffic_note"] = ("dram__bytes_read+write per step from profiles/r01_g_ncu_full_c3_fit_raw.csv: "
-                                                    "tcgen05 kernel 1.33 + 1.68 GB, weight-gradient sweep 1.51 GB (activation "
-                                                    "records written once, read twice, by design; rows themselves are 12.7 MB)")
+        if dp_check is not None:
+            line["dp_check"] = dp_check
         if wgrad_ms is not None:
             f_wgrad = sum(2 * (2 * H * ((D - (i & 1) + 1) // 2) + 2 * H * (D - (D - (i & 1) + 1) // 2 + Cd)) for i in range(L))
             rec_bytes = npad * L * eng.lib.rnvp_wgrad_record_floats(eng._desc) * 4
+            tk = (traffic or {}).get("kernels", {})
+            mma_ms = kms - wgrad_ms
             line["roofline"]["kernels"] = {
                 "rnvp_mma_kernel<16,8,32,0,1,2>": {
-                    "ms": kms - wgrad_ms, "algorithmic_flops_per_row": f_fit - f_wgrad,
-                    "tflops": per_gpu * (f_fit - f_wgrad) / ((kms - wgrad_ms) * 1e-3) / 1e12,
-                    "hbm_bytes_per_launch": per_gpu * bytes_row + per_gpu * L * D * 8 + rec_bytes,
-                    "note": "forward sweep + backward sweep (recompute, dgrad); writes the activation records"},
-                "rnvp_wgrad_kernel<3,2>": {
+                    "ms": mma_ms, "algorithmic_flops_per_row": f_fit - f_wgrad,
+                    "executed_tf32_tflops": 3 * per_gpu * (f_fit - f_wgrad) / (mma_ms * 1e-3) / 1e12,
+                    "frac_of_tf32_peak": 3 * per_gpu * (f_fit - f_wgrad) / (mma_ms * 1e-3) / 1e12 / tf32_peak,
+                    "frac_of_mufu_peak": per_gpu * 2 * n_tanh / (mma_ms * 1e-3) / mufu_peak,
+                    "designed_bytes_per_launch": per_gpu * bytes_row + per_gpu * L * D * 8 + rec_bytes + rec_bytes * 2 * H // eng.lib.rnvp_wgrad_record_floats(eng._desc),
+                    "measured_dram_bytes": tk.get("rnvp_mma_kernel", {}).get("dram_bytes"),
+                    "dram_frac_of_measured_peak": (tk["rnvp_mma_kernel"]["dram_bytes"] / (mma_ms * 1e-3) / 1e9 / hbm_peak) if "rnvp_mma_kernel" in tk else None,
+                    "bound": "latency / hand-offs: no unit above 0.6 (DESIGN.md 4.1c)",
+                    "note": "forward sweep + backward sweep (dgrad); writes the activation records, reads h back"},
+                "rnvp_wgrad_tc_kernel<32,24,16,2,4,4>": {
                     "ms": wgrad_ms, "algorithmic_flops_per_row": f_wgrad,
-                    "tflops": per_gpu * f_wgrad / (wgrad_ms * 1e-3) / 1e12,
-                    "hbm_bytes_per_launch": rec_bytes, "hbm_gbs": rec_bytes / (wgrad_ms * 1e-3) / 1e9,
-                    "hbm_frac_of_measured": rec_bytes / (wgrad_ms * 1e-3) / 1e9 / hbm_peak,
+                    "executed_tf32_tflops": 3 * per_gpu * f_wgrad / (wgrad_ms * 1e-3) / 1e12,
+                    "frac_of_tf32_peak": 3 * per_gpu * f_wgrad / (wgrad_ms * 1e-3) / 1e12 / tf32_peak,
+                    "algorithmic_bytes_per_launch": rec_bytes, "hbm_gbs": rec_bytes / (wgrad_ms * 1e-3) / 1e9,
+                    "hbm_frac_of_measured_peak": rec_bytes / (wgrad_ms * 1e-3) / 1e9 / hbm_peak,
+                    "measured_dram_bytes": tk.get("rnvp_wgrad_tc_kernel", {}).get("dram_bytes"),
+                    "bound": "dram (it streams the activation records once)",
                     "note": "timed alone on the last step's records"}}
-        mufu_peak = 16 * sms * sm_max * 1e6                             # MUFU lanes/s: the tanh (ex2 + rcp) pipe
-        n_tanh = 2 * H * L
         line["phases"] = {
             "log_prob": {"value": lp_rate, "unit": "rows/s", "kernel": fam, "rows_per_launch": n_pass, "kernel_ms": lp_ms,
-                         "flops_per_row": f_fwd, "frac_of_fp32_fma_peak": lp_rate / world * f_fwd / 1e12 / fp32_peak,
-                         "frac_of_mufu_peak": lp_rate / world * 2 * n_tanh / mufu_peak},
+                         "flops_per_row": f_fwd, "executed_tf32_tflops": 3 * lp_rate / world * f_fwd / 1e12,
+                         "frac_of_tf32_peak": 3 * lp_rate / world * f_fwd / 1e12 / tf32_peak,
+                         "frac_of_mufu_peak": lp_rate / world * 2 * n_tanh / mufu_peak,
+                         "frac_of_fp32_fma_peak_equivalent": lp_rate / world * f_fwd / 1e12 / fp32_peak,
+                         "hbm_frac_of_measured_peak": lp_rate / world * (4 * (D + Cd) + 4) / 1e9 / hbm_peak,
+                         "bound": "mufu + epilogue issue (tanh), DESIGN.md 4.1c"},
             "sample": {"value": s_rate, "unit": "rows/s", "kernel": fam, "rows_per_launch": n_pass, "kernel_ms": s_ms,
-                       "flops_per_row": f_fwd, "frac_of_fp32_fma_peak": s_rate / world * f_fwd / 1e12 / fp32_peak,
-                       "frac_of_mufu_peak": s_rate / world * 2 * n_tanh / mufu_peak,
-                       "note": "latent noise read from HBM (parity mode)"},
+                       "flops_per_row": f_fwd, "frac_of_mufu_peak": s_rate / world * 2 * n_tanh / mufu_peak,
+                       "hbm_frac_of_measured_peak": s_rate / world * (4 * (D + Cd)) / 1e9 / hbm_peak,
+                       "note": "prior draws generated in the kernel (Philox4x32-10 keyed on the global row index): rnvp_sample"},
+            "sample_from_noise": {"value": sn_rate, "unit": "rows/s", "kernel_ms": sn_ms,
+                                  "note": "parity mode: latent noise read from HBM (rnvp_inverse)"},
         }
         f2_fwd, _ = flops_per_row(D2, Cd2, L2, hid2[0])
         line["also"] = {"c2 -- " + desc2: {
-            "log_prob_rows_s": c2_lp, "sample_rows_s": c2_s, "rows_per_launch": n2, "kernel": "small-flow kernel (row per thread)",
+            "log_prob_rows_s": c2_lp, "sample_rows_s": c2_s, "sample_from_noise_rows_s": c2_sn, "rows_per_launch": n2,
+            "kernel": "small-flow kernel (row per thread)",
             "frac_of_mufu_peak": c2_lp / world * 2 * (2 * hid2[0] * L2) / mufu_peak,
+            "sample_frac_of_mufu_peak": c2_s / world * 2 * (2 * hid2[0] * L2) / mufu_peak,
             "frac_of_fp32_fma_peak": c2_lp / world * f2_fwd / 1e12 / fp32_peak,
-            "hbm_gbs": c2_lp / world * 16 / 1e9}}
+            "hbm_gbs": c2_lp / world * 16 / 1e9, "sample_hbm_gbs": c2_s / world * 12 / 1e9,
+            "bound": "mufu (2 per tanh, 320 per row)",
+            "note": "sample: in-kernel Philox noise, 4 B C + 8 B X per row; sample_from_noise additionally reads 8 B of noise"}}
         line["also"].update(others)
         if e2e:
             line["e2e"] = e2e

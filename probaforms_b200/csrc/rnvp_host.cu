@@ -18,9 +18,13 @@ namespace {
 
 template <typename T>
 void gather_range(const T* src, int64_t width, const int64_t* idx, int64_t row0, int64_t r0, int64_t r1, float* dst) {
-  constexpr int AHEAD = 8;                       // random rows: prefetch a few rows ahead of the copy
+  constexpr int AHEAD = 16;                      // random rows: prefetch every cache line of the row 16 rows ahead
+  const int64_t row_bytes = width * (int64_t)sizeof(T);
   for (int64_t r = r0; r < r1; ++r) {
-    if (idx && r + AHEAD < r1) __builtin_prefetch(src + idx[r + AHEAD] * width);
+    if (idx && r + AHEAD < r1) {
+      const char* nx = (const char*)(src + idx[r + AHEAD] * width);
+      for (int64_t b = 0; b < row_bytes; b += 64) __builtin_prefetch(nx + b);
+    }
     const T* s = src + (idx ? idx[r] : row0 + r) * width;
     float* d = dst + r * width;
     for (int64_t j = 0; j < width; ++j) d[j] = (float)s[j];

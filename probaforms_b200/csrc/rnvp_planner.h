@@ -135,7 +135,9 @@ inline void build_layout(FlowGeom* d) {
       d->m_w1_floats = (int)w1; d->m_w2_floats = (int)w2 + d->m_b2_floats;  // b2 images ride with the W2 copy
       // backward sweep (concurrent-net kernels only): K-major images of the transposed operands, per half-chunk of 16
       // units and net a [16 x 16] block [hi | lo]: W2T (units x transformed features) and W1T (x_K columns x units)
-      d->m_wt_floats = (!netseq && H % 16 == 0 && H <= 128) ? 4 * H * 16 : 0;
+      // (resident kernels).  Streamed kernels: per chunk step (net, chunk of CU units) a W2T block [hi | lo] of [CU x DH] and
+      // a W1T block [hi | lo] of [NTP x CU]; the tcgen05 weight-gradient sweep needs whole 128-unit lane blocks per net
+      d->m_wt_floats = (!netseq && H % 16 == 0 && H <= 128) ? 4 * H * 16 : ((streamed && H % 128 == 0) ? 4 * H * NTP : 0);
       d->m_layer_floats = d->m_w1_floats + d->m_w2_floats + 2 * d->m_wt_floats;
       d->mma_off = (d->packed + 31) & ~(int64_t)31;            // 128-byte aligned for the bulk copies
       d->mma_floats = (int64_t)d->L * d->m_layer_floats;
@@ -198,7 +200,25 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
           const int ft = lg.par == 0 ? 2 * r : 2 * r + 1;
           m2f[base3 + (net * 2 + part) * (NTP * 8) + mma_tiled_off(r, (DH + Cd) & 7, 8)] = (int)(4 * (g1.flat_b[net] + ft) + part);
         }
-    if (d->m_wt_floats) {
+    if (d->m_wt_floats && d->m_stream) {
+      // streamed backward images, indexed by chunk step cc = net * NC + c
+      const int64_t base4 = base2 + d->m_w2_floats, base5 = base4 + d->m_wt_floats;
+      for (int net = 0; net < 2; ++net)
+        for (int c = 0; c < NC; ++c)
+          for (int part = 0; part < 2; ++part) {
+            const int64_t cc = (int64_t)net * NC + c;
+            const int64_t o2 = base4 + (cc * 2 + part) * ((int64_t)CU * NTP);     // W2T block: [CU units x NTP (e, K)]
+            const int64_t o1 = base5 + (cc * 2 + part) * ((int64_t)NTP * CU);     // W1T block: [NTP (x_K col) x CU units (K)]
+            for (int un = 0; un < CU; ++un)
+              for (int e = 0; e < DH; ++e) {
+                const int unit = c * CU + un;
+                const int ft = lg.par == 0 ? 2 * e : 2 * e + 1;            // transformed feature e
+                const int xk = lg.par == 0 ? 2 * e + 1 : 2 * e;            // conditioning feature e
+                m2f[o2 + mma_tiled_off(un, e, NTP)] = (int)(4 * (g1.flat_w[net] + (int64_t)ft * H + unit) + part);
+                m2f[o1 + mma_tiled_off(e, un, CU)] = (int)(4 * (g0.flat_w[net] + (int64_t)unit * (D + Cd) + xk) + part);
+              }
+          }
+    } else if (d->m_wt_floats) {
       const int64_t base4 = base2 + d->m_w2_floats, base5 = base4 + d->m_wt_floats;
       for (int hc = 0; hc < H / 16; ++hc)
         for (int net = 0; net < 2; ++net)

@@ -16,7 +16,13 @@
 //   * warps 4-11 are the epilogue: TWO THREADS PER ROW (a thread cannot hold a 128-D row): thread (row, half) owns half of
 //     the transformed and half of the conditioning features, writes its half of u, converts its 16 columns of every D1
 //     chunk and applies the coupling to its 32 features; the two partial log-dets / squared norms meet in shared memory.
-// Reference semantics: RealNVPLayer.f / .g (realnvp.py:73-129) looped as in nflow.py:109-115 / 142-143.
+//   MODE 2 (fit step): the forward sweep additionally stashes (x_T, s) per layer and writes h = act(.) and u = [x_K, c] into
+//   the activation record of (layer, row) (rnvp_wgrad_tc.cu); the same CTA then walks the layers BACKWARDS with the same
+//   thread ownership, streaming the transposed chunk images: delta2 from the stash -> TMEM (hi/lo, 4 DH columns), per chunk
+//   step dh = delta2 W2 (tensor core), delta1 = dh * act'(h) with h read back from the record, du += delta1 W1[:, x_K]
+//   (merged A_hi x [B_hi ; B_lo]); delta2 completes the record, and rnvp_wgrad_tc_kernel contracts the records over rows.
+// Reference semantics: RealNVPLayer.f / .g (realnvp.py:73-129) looped as in nflow.py:109-115 / 142-143; MODE 2 is the
+// autograd backward of loss = -nf.log_prob(X, C) (realnvp.py:246-250) up to the weight-gradient contraction.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tc05.cuh"
@@ -61,6 +67,9 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
   constexpr int D2C = D1B + 4 * CU, C2C = D2C + NTP, TCOLS = C2C + NTP;
   static_assert(TCOLS <= 512, "TMEM budget");
   static_assert(DH % 16 == 0 && (K1PMAX - DH) % 8 == 0 && CU == 32, "layout assumptions");
+  // backward sweep (MODE 2): delta2 hi / lo (2 DH columns each), the dh / delta1 chunk ring, the du accumulators [main | corr]
+  constexpr int E2H = 0, E2L = 2 * DH, DHB = 4 * DH, DUM = DHB + 4 * CU, DUC = DUM + NTP;
+  static_assert(DUC + NTP <= 512, "TMEM budget (backward)");
 
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -70,7 +79,9 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
   const int nL = a.l1 - a.l0;
   const int w1c = 2 * CU * K1P;                         // floats of one W1 chunk image [hi | lo]
   constexpr int W2C = 2 * NTP * CU, B2C = 2 * NTP * 8;  // W2 chunk image [hi | lo]; b2 image of one net [hi | lo]
-  const int stage_floats = ((2 * CU * K1PMAX + W2C + B2C) + 31) & ~31;
+  const int stage_floats = ((2 * CU * K1PMAX + W2C + B2C) + 31) & ~31;      // >= the backward stage: W2T + W1T chunk = 2 * W2C
+  const bool do_bwd = MODE == 2 && a.do_bwd;
+  const int n_sweeps = do_bwd ? 2 : 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + WD_STAGES * stage_floats);
   float* xch = reinterpret_cast<float*>(bars + WB_COUNT);                 // [128][2]: partial (logdet, |z|^2) of the second half-thread
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xch + 256);
@@ -96,23 +107,32 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
       long long step = 0;
       const uint32_t w1c_bytes = (uint32_t)w1c * 4u, w2c_bytes = (uint32_t)W2C * 4u, b2_bytes = (uint32_t)B2C * 4u;
       for (int it = 0; it < my_tiles; ++it)
-        for (int li = 0; li < nL; ++li) {
-          const int i = MODE == 1 ? a.l1 - 1 - li : a.l0 + li;
-          const float* L0 = a.wimg + (size_t)i * a.layer_floats;
-          const float* W2 = L0 + a.w1_floats;
-          const float* B2 = W2 + (size_t)4 * NTP * H;
-          for (int cc = 0; cc < NCS; ++cc, ++step) {
-            const int st = (int)(step % WD_STAGES);
-            if (step >= WD_STAGES) mbar_wait_relaxed(&bars[WB_WE + st], (uint32_t)((step / WD_STAGES - 1) & 1));
-            const int net = cc >= NC ? 1 : 0, c = cc - net * NC;
-            float* dst = sm + (size_t)st * stage_floats;
-            const bool with_b2 = c == 0;
-            mbar_expect_tx(&bars[WB_WF + st], w1c_bytes + w2c_bytes + (with_b2 ? b2_bytes : 0u));
-            bulk_g2s(dst, L0 + (size_t)cc * w1c, w1c_bytes, &bars[WB_WF + st]);
-            bulk_g2s(dst + 2 * CU * K1PMAX, W2 + (size_t)(c * 2 + net) * W2C, w2c_bytes, &bars[WB_WF + st]);
-            if (with_b2) bulk_g2s(dst + 2 * CU * K1PMAX + W2C, B2 + (size_t)net * B2C, b2_bytes, &bars[WB_WF + st]);
+        for (int sw = 0; sw < n_sweeps; ++sw)
+          for (int li = 0; li < nL; ++li) {
+            const int i = (MODE == 1 || sw == 1) ? a.l1 - 1 - li : a.l0 + li;
+            const float* L0 = a.wimg + (size_t)i * a.layer_floats;
+            const float* W2 = L0 + a.w1_floats;
+            const float* B2 = W2 + (size_t)4 * NTP * H;
+            const float* W2T = W2 + a.w2_floats;                   // streamed backward images: [cc][hi | lo][CU x NTP]
+            const float* W1T = W2T + a.wt_floats;                  //                           [cc][hi | lo][NTP x CU]
+            for (int cc = 0; cc < NCS; ++cc, ++step) {
+              const int st = (int)(step % WD_STAGES);
+              if (step >= WD_STAGES) mbar_wait_relaxed(&bars[WB_WE + st], (uint32_t)((step / WD_STAGES - 1) & 1));
+              const int net = cc >= NC ? 1 : 0, c = cc - net * NC;
+              float* dst = sm + (size_t)st * stage_floats;
+              if (sw == 0) {
+                const bool with_b2 = c == 0;
+                mbar_expect_tx(&bars[WB_WF + st], w1c_bytes + w2c_bytes + (with_b2 ? b2_bytes : 0u));
+                bulk_g2s(dst, L0 + (size_t)cc * w1c, w1c_bytes, &bars[WB_WF + st]);
+                bulk_g2s(dst + 2 * CU * K1PMAX, W2 + (size_t)(c * 2 + net) * W2C, w2c_bytes, &bars[WB_WF + st]);
+                if (with_b2) bulk_g2s(dst + 2 * CU * K1PMAX + W2C, B2 + (size_t)net * B2C, b2_bytes, &bars[WB_WF + st]);
+              } else {
+                mbar_expect_tx(&bars[WB_WF + st], 2 * w2c_bytes);
+                bulk_g2s(dst, W2T + (size_t)cc * W2C, w2c_bytes, &bars[WB_WF + st]);
+                bulk_g2s(dst + W2C, W1T + (size_t)cc * W2C, w2c_bytes, &bars[WB_WF + st]);
+              }
+            }
           }
-        }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer

@@ -28,7 +28,7 @@ import torch
 def host_threads():
     """Host threads one process may use for gathers / copies: the box's cores shared by the local ranks."""
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return max(1, min(8, (os.cpu_count() or 1) // max(local_world, 1)))
+    return max(1, min(16, (os.cpu_count() or 1) // max(local_world, 1) - 1))
 
 
 def host_rows(A):
