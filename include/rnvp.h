@@ -63,7 +63,8 @@ int64_t rnvp_workspace_bytes(const rnvp_desc* d, int64_t N);
  * n = 4*(n_hidden+1)*L entries pairs.  Returns the number of tensors. */
 int rnvp_param_tensors(const rnvp_desc* d, int64_t* offsets, int max_tensors);
 /* plan introspection: mode 0 forward, 1 inverse, 2 fused forward+backward, 3 backward-only sweep (used after the
- * tcgen05 forward); rows per CTA tile, shared memory, ops per tile, kernel family (0 tile, 1 small-flow, 2 tcgen05) */
+ * tcgen05 forward), 4 = "is the whole fit step on the tensor cores" (kernel_family 2 iff yes); rows per CTA tile, shared
+ * memory, ops per tile of the FP32 program, kernel family (0 tile, 1 small-flow, 2 tcgen05) */
 int rnvp_plan_info(const rnvp_desc* d, int mode, int* tile_rows, int* smem_bytes, int* n_ops, int* kernel_family);
 
 /* flat (reference layout) -> packed; run after every parameter update */

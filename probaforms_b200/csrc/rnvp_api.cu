@@ -264,6 +264,9 @@ bool use_mma(const rnvp_desc* d) { return d->mma_ok && d->path != 1; }
 bool use_mma_bwd(const rnvp_desc* d) { return use_mma(d) && d->m_wt_floats > 0; }
 // forward sweep of a fit step on the tensor cores (stash for the FP32 backward sweep): resident-image kernels only
 bool use_mma_fwd_stash(const rnvp_desc* d) { return use_mma(d) && !d->m_stream; }
+// rows covered by the record / stash arrays of a tensor-core fit step: whole row tiles of the sweep kernel (pairs of 128-row
+// tiles in rnvp_mma.cu, single tiles in rnvp_wide.cu), so that the weight-gradient sweep never reads an unwritten record
+int64_t fit_npad(const rnvp_desc* d, int64_t N) { return d->m_netseq ? (N + 127) / 128 * 128 : (N + 255) / 256 * 256; }
 // record stride of the activation records exchanged between the backward sweep and the weight-gradient sweep
 int wgrad_rec_floats(const rnvp_desc* d) {
   const int K1P = (d->mDH + d->Cd + 7) & ~7;
@@ -288,12 +291,12 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.wt_floats = records ? d->m_wt_floats : 0;
   a.trace = g_mma_trace;
   a.seed = seed; a.row_offset = row_offset;
-  if (d->m_stream) {
-    if (mode == 2) return fail(RNVP_ESHAPE, "streamed tcgen05 kernels have no fit sweep");
+  if (d->m_stream || (d->m_netseq && mode == 2 && records)) {     // wide kernels: streamed images; the fit sweeps of every D >= 64 flow
+    if (mode == 2 && !records) return fail(RNVP_ESHAPE, "streamed tcgen05 kernels run the fit step with their own backward sweep only");
     const long long tiles = (N + 127) / 128;
     if (tiles > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
     a.n_pairs = (int)tiles;                      // rnvp_wide.cu walks single 128-row tiles
-    a.wt_floats = 0;
+    if (records) { a.rec = wgrad_rec_floats(d); a.Npad = fit_npad(d, N); }
     cudaError_t e = rnvp_launch_wide(d->mDH, d->act, mode, a, (int)std::min<long long>(tiles, d->num_sms), stream);
     if (e != cudaSuccess) return cuda_fail(e, "tcgen05 streamed kernel launch");
     return 0;
@@ -422,7 +425,7 @@ int64_t rnvp_workspace_bytes(const rnvp_desc* dc, int64_t N) {
   if (!d) return -1;
   if (use_small_fit(d)) return 16;                      // the row-per-thread fit kernel keeps its stash in local memory
   if (use_mma_bwd(d)) {
-    const int64_t n = std::max<int64_t>(N, 1), npad = (n + 255) / 256 * 256;
+    const int64_t n = std::max<int64_t>(N, 1), npad = fit_npad(d, n);
     return (npad * d->L * 2 * d->mDH + (int64_t)d->L * npad * wgrad_rec_floats(d)) * 4;
   }
   if (use_mma_fwd_stash(d)) return std::max<int64_t>(N, 1) * (d->D + (int64_t)d->L * 2 * d->mDH) * 4;
@@ -452,12 +455,16 @@ int rnvp_plan_info(const rnvp_desc* dc, int mode, int* tile_rows, int* smem_byte
   if (check_desc(d)) return RNVP_EINVAL;
   if (mode < 0 || mode > 4) return fail(RNVP_EINVAL, "mode must be 0..4");
   Program* p = nullptr;
-  int rc = get_program(d, mode, 0, d->L, &p);
+  int rc = get_program(d, mode == 4 ? 2 : mode, 0, d->L, &p);
   if (rc) return rc;
   if (tile_rows) *tile_rows = 8 * p->TR;
   if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
   if (n_ops) *n_ops = p->n_ops;
-  if (kernel_family) *kernel_family = (mode >= 2 ? use_mma_fwd_stash(d) : use_mma(d)) ? 2 : (((mode < 2 && d->small_ok) || (mode == 2 && use_small_fit(d))) ? 1 : 0);
+  if (mode == 4) {          // pseudo-mode: does the whole fit step run on the tensor cores (sweeps + weight gradients)?
+    if (kernel_family) *kernel_family = use_mma_bwd(d) ? 2 : 0;
+    return 0;
+  }
+  if (kernel_family) *kernel_family = (mode >= 2 ? (use_mma_fwd_stash(d) || use_mma_bwd(d)) : use_mma(d)) ? 2 : (((mode < 2 && d->small_ok) || (mode == 2 && use_small_fit(d))) ? 1 : 0);
   return 0;
 }
 
@@ -555,7 +562,7 @@ int rnvp_backward(const rnvp_desc* dc, const float* d_packed, const float* d_X, 
                      (cudaStream_t)stream, d_gpacked, d_logp_sum, scale);
   if (use_mma_bwd(d) && N > 0) {
     // forward + backward sweeps in one tcgen05 launch (per-layer records to the workspace), then the weight-gradient sweep
-    const int64_t npad = (N + 255) / 256 * 256;
+    const int64_t npad = fit_npad(d, N);
     const int64_t stash_f = npad * d->L * 2 * d->mDH, rec_f = (int64_t)d->L * npad * wgrad_rec_floats(d);   // both blocked by 32 rows
     if (!d_workspace || workspace_bytes < (stash_f + rec_f) * 4)
       return fail(RNVP_EINVAL, "rnvp_backward: workspace too small (see rnvp_workspace_bytes)");
@@ -618,12 +625,13 @@ int rnvp_wgrad_sweep(const rnvp_desc* dc, const float* d_packed, int64_t Npad, c
                      void* stream) {
   rnvp_desc* d = const_cast<rnvp_desc*>(dc);
   if (check_desc(d)) return RNVP_EINVAL;
-  if (!d->mma_ok || 2 * d->hidden[0] > 256 || d->hidden[0] % 16)
-    return fail(RNVP_ESHAPE, "rnvp_wgrad_sweep: needs a tcgen05-eligible flow with hidden width <= 128 (multiple of 16)");
+  if (!d->mma_ok || d->m_wt_floats == 0)
+    return fail(RNVP_ESHAPE, "rnvp_wgrad_sweep: needs a flow whose fit step runs on the tensor cores (D = 32 with H <= 128, or a "
+                             "wide flow with H a multiple of 128)");
   if (!d_records || !d_gpacked || !d_packed) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: null buffer");
   if (Npad <= 0 || Npad % 32) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: Npad must be a positive multiple of 32");
   const int K1P = (d->mDH + d->Cd + 7) & ~7, TP = d->mDH;
-  if (!d->wgrad_legacy) {
+  if (!d->wgrad_legacy || d->m_netseq) {
     // tcgen05 sweep: one CTA per (layer, block of 128 hidden units of [nn_t | nn_s], row slice), one wave of CTAs
     RnvpWgradTcArgs a;
     a.gR = d_records; a.rec = wgrad_rec_floats(d); a.Npad = Npad; a.H = d->hidden[0];

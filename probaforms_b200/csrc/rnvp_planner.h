@@ -137,7 +137,8 @@ inline void build_layout(FlowGeom* d) {
       // units and net a [16 x 16] block [hi | lo]: W2T (units x transformed features) and W1T (x_K columns x units)
       // (resident kernels).  Streamed kernels: per chunk step (net, chunk of CU units) a W2T block [hi | lo] of [CU x DH] and
       // a W1T block [hi | lo] of [NTP x CU]; the tcgen05 weight-gradient sweep needs whole 128-unit lane blocks per net
-      d->m_wt_floats = (!netseq && H % 16 == 0 && H <= 128) ? 4 * H * 16 : ((streamed && H % 128 == 0) ? 4 * H * NTP : 0);
+      // (D = 64 flows with resident images, e.g. c4, run their FIT step on the streamed kernels too: same chunk images)
+      d->m_wt_floats = (!netseq && H % 16 == 0 && H <= 128) ? 4 * H * 16 : ((netseq && H % 128 == 0) ? 4 * H * NTP : 0);
       d->m_layer_floats = d->m_w1_floats + d->m_w2_floats + 2 * d->m_wt_floats;
       d->mma_off = (d->packed + 31) & ~(int64_t)31;            // 128-byte aligned for the bulk copies
       d->mma_floats = (int64_t)d->L * d->m_layer_floats;
@@ -200,7 +201,7 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
           const int ft = lg.par == 0 ? 2 * r : 2 * r + 1;
           m2f[base3 + (net * 2 + part) * (NTP * 8) + mma_tiled_off(r, (DH + Cd) & 7, 8)] = (int)(4 * (g1.flat_b[net] + ft) + part);
         }
-    if (d->m_wt_floats && d->m_stream) {
+    if (d->m_wt_floats && d->m_netseq) {
       // streamed backward images, indexed by chunk step cc = net * NC + c
       const int64_t base4 = base2 + d->m_w2_floats, base5 = base4 + d->m_wt_floats;
       for (int net = 0; net < 2; ++net)

@@ -35,4 +35,4 @@ struct RnvpWgradTcArgs {
   long long* trace;                // development aid (rnvp_debug_set_trace): wait accounting of CTA 0
   int one_issuer;                  // development knob: issuer A also issues the dW2 products (issuer B idles)
 };
-size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, int K1P8);
+size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, int K1P8, int NN);

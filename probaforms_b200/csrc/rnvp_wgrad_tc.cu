@@ -73,18 +73,24 @@ __device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(_
 
 // NU: columns of the dW1 tile (>= K1P8, multiple of 16); K1P8: u columns of a record; TP: delta2 columns per net (multiple of 16)
 // NBUF: TMEM staging buffers; NOP: operand buffers in shared memory; NSLOT: raw ring depth
-template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT>
-__global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __grid_constant__ RnvpWgradTcArgs a) {
+template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT, bool SINGLE>
+__global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __grid_constant__ RnvpWgradTcArgs a) {
   // TMEM column map.  Per net the gradient accumulators sit side by side, [main | corr]: A_hi x [B_hi ; B_lo] is ONE MMA of
   // twice the width (the hi and lo operand tiles are adjacent in shared memory), A_lo x B_hi adds into the corr half.
-  constexpr int W2H = 0, W2L = 2 * TP, STG0 = 4 * TP, STGW = 128;               // staging: DH/D1H +0, D1L +32, HH +64, HL +96
-  constexpr int ACC1 = STG0 + NBUF * STGW, ACC2 = ACC1 + 2 * NU, TCOLS = ACC2 + 4 * TP;
+  // SINGLE (wide flows, H % 128 == 0: every lane block belongs to one net): only the block's own net's delta2 / W2 columns
+  // are staged, and main products and corrections share ONE accumulator per product (TMEM columns: 416 for c5)
+  constexpr int NN = SINGLE ? 1 : 2;
+  constexpr bool MERGED = !SINGLE;
+  constexpr int NTHR = SINGLE ? 384 : WT_THREADS;          // SINGLE: one issuer (warp 0), the TMA producer takes warp 1: 12 warps, 168 registers
+  const bool one_issuer = SINGLE || a.one_issuer;
+  constexpr int W2H = 0, W2L = NN * TP, STG0 = 2 * NN * TP, STGW = 128;         // staging: DH/D1H +0, D1L +32, HH +64, HL +96
+  constexpr int ACC1 = STG0 + NBUF * STGW, ACC2 = ACC1 + (MERGED ? 2 * NU : NU), TCOLS = ACC2 + (MERGED ? 4 * TP : TP);
   static_assert(TCOLS <= 512, "TMEM budget");
   static_assert(NU % 16 == 0 && TP % 16 == 0 && K1P8 % 8 == 0 && K1P8 <= NU, "N of an M=128 MMA is a multiple of 16");
-  constexpr int UB = (NU / 8) * WT_NG, EBN = (TP / 8) * WT_NG, DK = WT_ROWS * 2 * TP;   // floats of one hi (or lo) tile
-  constexpr int OPF = 2 * UB + 4 * EBN + 2 * DK;                                  // floats of one operand buffer
+  constexpr int UB = (NU / 8) * WT_NG, EBN = (TP / 8) * WT_NG, DK = WT_ROWS * NN * TP;  // floats of one hi (or lo) tile
+  constexpr int OPF = 2 * UB + 2 * NN * EBN + 2 * DK;                             // floats of one operand buffer
   // operand buffer: [u_hi | u_lo | e_t_hi | e_t_lo | e_s_hi | e_s_lo | dk_hi | dk_lo]
-  constexpr int RAW_H = WT_ROWS * 128, RAW_U = WT_ROWS * K1P8, RAW_E = WT_ROWS * 2 * TP, RAW = RAW_H + RAW_U + RAW_E;
+  constexpr int RAW_H = WT_ROWS * 128, RAW_U = WT_ROWS * K1P8, RAW_E = WT_ROWS * NN * TP, RAW = RAW_H + RAW_U + RAW_E;
 
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -115,13 +121,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 10); }
-    for (int b = 0; b < NOP; ++b) { mbar_init(&b_conv[b], 64); mbar_init(&b_opfree[b], a.one_issuer ? 1 : 2); }
+    for (int b = 0; b < NOP; ++b) { mbar_init(&b_conv[b], 64); mbar_init(&b_opfree[b], one_issuer ? 1 : 2); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(&b_dh[b], 1); mbar_init(&b_hfree[b], 1); mbar_init(&b_afull[b], 256); }
-    mbar_init(b_accfull, a.one_issuer ? 1 : 2); mbar_init(b_accfree, 256);
+    mbar_init(b_accfull, one_issuer ? 1 : 2); mbar_init(b_accfree, 256);
     mbar_fence_init();
   }
   // zero the operand buffers once: padding columns (K1P8..NU) and padding K-groups are never written again
-  for (int i = tid; i < NOP * OPF; i += WT_THREADS) op[i] = 0.0f;
+  for (int i = tid; i < NOP * OPF; i += NTHR) op[i] = 0.0f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   fence_before_sync();
   __syncthreads();
@@ -139,21 +145,21 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
     const bool leader = elect_one();
     const uint32_t idesc_dh = idesc_tf32(128, WT_ROWS), idesc_u = idesc_tf32(128, NU), idesc_u2 = idesc_tf32(128, 2 * NU);
     const uint32_t op_addr = smem_u32(op);
-    const int kj0 = net_lo * (TP / 8), kj1 = (net_hi + 1) * (TP / 8);     // K steps of the dh product that are not all-zero
+    const int kj0 = SINGLE ? 0 : net_lo * (TP / 8), kj1 = SINGLE ? TP / 8 : (net_hi + 1) * (TP / 8);   // K steps of the dh product that are not all-zero
     // dh^T of stage s -> staging buffer s % NBUF: A = W2^T image (TMEM), B = delta2 [N = rows, K = 2TP] (core-matrix tiled)
     auto issue_dh = [&](int s) {
       const int b = s % NBUF, ob = s % NOP;
-      const uint32_t dk_hi = op_addr + (uint32_t)(ob * OPF + 2 * UB + 4 * EBN) * 4u, dk_lo = dk_hi + (uint32_t)DK * 4u;
+      const uint32_t dk_hi = op_addr + (uint32_t)(ob * OPF + 2 * UB + 2 * NN * EBN) * 4u, dk_lo = dk_hi + (uint32_t)DK * 4u;
       const uint32_t d = tbase + STG0 + b * STGW;
-      constexpr uint32_t SBOD = (2 * TP / 4) * 128u;
+      constexpr uint32_t SBOD = (NN * TP / 4) * 128u;
 #pragma unroll
-      for (int j = 0; j < 2 * TP / 8; ++j)
+      for (int j = 0; j < NN * TP / 8; ++j)
         if (j >= kj0 && j < kj1) mma_tf32_ts(d, tbase + W2L + 8 * j, desc(dk_hi + 256u * j, 128u, SBOD), idesc_dh, j > kj0 ? 1u : 0u);
 #pragma unroll
-      for (int j = 0; j < 2 * TP / 8; ++j)
+      for (int j = 0; j < NN * TP / 8; ++j)
         if (j >= kj0 && j < kj1) mma_tf32_ts(d, tbase + W2H + 8 * j, desc(dk_lo + 256u * j, 128u, SBOD), idesc_dh, 1u);
 #pragma unroll
-      for (int j = 0; j < 2 * TP / 8; ++j)
+      for (int j = 0; j < NN * TP / 8; ++j)
         if (j >= kj0 && j < kj1) mma_tf32_ts(d, tbase + W2H + 8 * j, desc(dk_hi + 256u * j, 128u, SBOD), idesc_dh, 1u);
     };
     uint32_t ph_conv = 0, ph_afull = 0, ph_accfree = 0;          // one phase bit per ring entry
@@ -178,20 +184,33 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
         const long long tq0 = wa.on ? clock64() : 0;
 #pragma unroll
         for (int j = 0; j < WT_ROWS / 8; ++j) {
-          mma_tf32_ts(tbase + ACC1, stg + 0 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u2, (first_in_grp && j == 0) ? 0u : 1u);   // d1_hi x [u_hi ; u_lo]
-          mma_tf32_ts(tbase + ACC1 + NU, stg + 32 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u, 1u);                               // d1_lo x u_hi
+          const uint32_t acc = (first_in_grp && j == 0) ? 0u : 1u;
+          if (MERGED) {
+            mma_tf32_ts(tbase + ACC1, stg + 0 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u2, acc);               // d1_hi x [u_hi ; u_lo]
+            mma_tf32_ts(tbase + ACC1 + NU, stg + 32 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u, 1u);           // d1_lo x u_hi
+          } else {
+            mma_tf32_ts(tbase + ACC1, stg + 0 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u, acc);                // d1_hi x u_hi
+            mma_tf32_ts(tbase + ACC1, stg + 32 + 8 * j, desc(ub + KS * j, LBO, SBO), idesc_u, 1u);                // d1_lo x u_hi
+            mma_tf32_ts(tbase + ACC1, stg + 0 + 8 * j, desc(ub + (uint32_t)UB * 4u + KS * j, LBO, SBO), idesc_u, 1u);   // d1_hi x u_lo
+          }
         }
         if (wa.on) wa.t[4] += clock64() - tq0;
-        if (a.one_issuer) {
+        if (one_issuer) {
           const uint32_t eb = ub + (uint32_t)(2 * UB) * 4u;
           const uint32_t idesc_e = idesc_tf32(128, TP), idesc_e2 = idesc_tf32(128, 2 * TP);
 #pragma unroll
           for (int j = 0; j < WT_ROWS / 8; ++j) {
             const uint32_t acc = (first_in_grp && j == 0) ? 0u : 1u;
-            for (int n = net_lo; n <= net_hi; ++n) {
-              const uint32_t ebn = eb + (uint32_t)(n * 2 * EBN) * 4u, d2 = tbase + ACC2 + n * 2 * TP;
-              mma_tf32_ts(d2, stg + 64 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e2, acc);
-              mma_tf32_ts(d2 + TP, stg + 96 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e, 1u);
+            if (MERGED) {
+              for (int n = net_lo; n <= net_hi; ++n) {
+                const uint32_t ebn = eb + (uint32_t)(n * 2 * EBN) * 4u, d2 = tbase + ACC2 + n * 2 * TP;
+                mma_tf32_ts(d2, stg + 64 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e2, acc);
+                mma_tf32_ts(d2 + TP, stg + 96 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e, 1u);
+              }
+            } else {
+              mma_tf32_ts(tbase + ACC2, stg + 64 + 8 * j, desc(eb + KS * j, LBO, SBO), idesc_e, acc);
+              mma_tf32_ts(tbase + ACC2, stg + 96 + 8 * j, desc(eb + KS * j, LBO, SBO), idesc_e, 1u);
+              mma_tf32_ts(tbase + ACC2, stg + 64 + 8 * j, desc(eb + (uint32_t)EBN * 4u + KS * j, LBO, SBO), idesc_e, 1u);
             }
           }
           mma_commit(&b_hfree[b]);
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
       }
     }
     if (leader) wa.flush(a.trace, 0, clock64() - tstart);
-  } else if (warp == 1) {
+  } else if (warp == 1 && !SINGLE) {
     // ------------------------------------------------------------------ issuer B: dW2 (issuing, not the tensor pipe, bounds
     // these small MMAs -- ~35 cycles each -- so the gradient products are split over two issuing threads)
     const bool leader = elect_one();
@@ -238,10 +257,16 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
 #pragma unroll
         for (int j = 0; j < WT_ROWS / 8; ++j) {
           const uint32_t acc = (first_in_grp && j == 0) ? 0u : 1u;
-          for (int n = net_lo; n <= net_hi; ++n) {
-            const uint32_t ebn = eb + (uint32_t)(n * 2 * EBN) * 4u, d2 = tbase + ACC2 + n * 2 * TP;
-            mma_tf32_ts(d2, stg + 64 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e2, acc);                  // h_hi x [e_hi ; e_lo]
-            mma_tf32_ts(d2 + TP, stg + 96 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e, 1u);               // h_lo x e_hi
+          if (MERGED) {
+            for (int n = net_lo; n <= net_hi; ++n) {
+              const uint32_t ebn = eb + (uint32_t)(n * 2 * EBN) * 4u, d2 = tbase + ACC2 + n * 2 * TP;
+              mma_tf32_ts(d2, stg + 64 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e2, acc);                // h_hi x [e_hi ; e_lo]
+              mma_tf32_ts(d2 + TP, stg + 96 + 8 * j, desc(ebn + KS * j, LBO, SBO), idesc_e, 1u);             // h_lo x e_hi
+            }
+          } else {
+            mma_tf32_ts(tbase + ACC2, stg + 64 + 8 * j, desc(eb + KS * j, LBO, SBO), idesc_e, acc);          // h_hi x e_hi
+            mma_tf32_ts(tbase + ACC2, stg + 96 + 8 * j, desc(eb + KS * j, LBO, SBO), idesc_e, 1u);           // h_lo x e_hi
+            mma_tf32_ts(tbase + ACC2, stg + 64 + 8 * j, desc(eb + (uint32_t)EBN * 4u + KS * j, LBO, SBO), idesc_e, 1u);   // h_hi x e_lo
           }
         }
         mma_commit(&b_opfree[ob]);
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
       __syncwarp();
     }
     if (leader) wa.flush(a.trace, 1, clock64() - tstart);
-  } else if (warp == 12) {
+  } else if (warp == (SINGLE ? 1 : 12)) {
     // ------------------------------------------------------------------ TMA producer: three bulk copies per stage
     if (lane == 0) {
       const uint32_t bytes_h = (uint32_t)(WT_ROWS * ncols_h) * 4u;
@@ -265,15 +290,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
         mbar_expect_tx(&b_full[slot], bytes_h + (uint32_t)(RAW_U + RAW_E) * 4u);
         bulk_g2s(dst, src + (size_t)WT_ROWS * 128 * mb, bytes_h, &b_full[slot]);
         bulk_g2s(dst + RAW_H, src + (size_t)WT_ROWS * H2, (uint32_t)RAW_U * 4u, &b_full[slot]);
-        bulk_g2s(dst + RAW_H + RAW_U, src + (size_t)WT_ROWS * (H2 + K1P8), (uint32_t)RAW_E * 4u, &b_full[slot]);
+        bulk_g2s(dst + RAW_H + RAW_U, src + (size_t)WT_ROWS * (H2 + K1P8 + (SINGLE ? net_lo * TP : 0)), (uint32_t)RAW_E * 4u, &b_full[slot]);
       }
       wa.flush(a.trace, 4, clock64() - tstart);
     }
   } else if (warp < 4) {
     // ------------------------------------------------------------------ converters (lanes = rows)
     const int cw = warp - 2;
-    constexpr int NCGU = K1P8 / 4, NCGE = (2 * TP) / 4, NUW = (NCGU + 1) / 2, NEW = NCGE / 2;
-    const int cg_u0 = H2 >> 2, cg_e0 = (H2 + K1P8) >> 2;                  // global column-group index (the slot swizzle uses it)
+    constexpr int NCGU = K1P8 / 4, NCGE = (NN * TP) / 4, NUW = (NCGU + 1) / 2, NEW = NCGE / 2;
+    const int cg_u0 = H2 >> 2, cg_e0 = (H2 + K1P8 + (SINGLE ? net_lo * TP : 0)) >> 2;                  // global column-group index (the slot swizzle uses it)
     float db2[NEW][4];
 #pragma unroll
     for (int i = 0; i < NEW; ++i) db2[i][0] = db2[i][1] = db2[i][2] = db2[i][3] = 0.0f;
@@ -302,7 +327,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
       if (s >= NOP) { wa.wait(&b_opfree[ob], (ph_free >> ob) & 1u, 1); ph_free ^= 1u << ob; }      // the MMAs that read this buffer are done
       float* ub_hi = op + ob * OPF;
       float* eb = ub_hi + 2 * UB;
-      float* dk_hi = eb + 4 * EBN;
+      float* dk_hi = eb + 2 * NN * EBN;
 #pragma unroll
       for (int i = 0; i < NUW; ++i) {
         const int cg = cw + 2 * i;
@@ -330,7 +355,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
           db2[i][q] += vv[q];
         }
         // operand of the dh product: [N = rows, K = 2TP], core matrices of 8 rows x 4 columns
-        const int o2 = (r >> 3) * (2 * TP / 4) * 32 + cg * 32 + (r & 7) * 4;
+        const int o2 = (r >> 3) * (NN * TP / 4) * 32 + cg * 32 + (r & 7) * 4;
         *reinterpret_cast<float4*>(dk_hi + o2) = ve[i];
         *reinterpret_cast<float4*>(dk_hi + DK + o2) = make_float4(lo_part(vv[0]), lo_part(vv[1]), lo_part(vv[2]), lo_part(vv[3]));
       }
@@ -341,7 +366,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
     }
     if (lane == 0) wa.flush(a.trace, 2, clock64() - tstart);
     // db2[e] = sum over this CTA's rows of delta2[:, e]; the CTA of lane block 0 contributes it
-    if (mb == 0 && nst > 0) {
+    if ((SINGLE ? 128 * mb == net_lo * H : mb == 0) && nst > 0) {
       const RnvpWgradLayer& lw = a.layers[layer];
 #pragma unroll
       for (int i = 0; i < NEW; ++i) {
@@ -351,7 +376,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
           float v = db2[i][q];
 #pragma unroll
           for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-          const int e = 4 * cg + q, net = e / TP, ee = e - net * TP;
+          const int e = 4 * cg + q, nl = e / TP, ee = e - nl * TP, net = SINGLE ? net_lo : nl;
           if (lane == 0 && ee < a.nT) atomicAdd(a.gpacked + lw.b2_off[net] + ee, v);
         }
       }
@@ -369,13 +394,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
     {
       const float* w2 = a.packed + lw.w2_off[net];
 #pragma unroll
-      for (int e0 = half * TP; e0 < (half + 1) * TP; e0 += 8) {          // half 0 writes the e_t columns, half 1 the e_s columns
+      for (int e0 = half * (NN * TP / 2); e0 < (half + 1) * (NN * TP / 2); e0 += 8) {   // the two threads of a lane share the image columns
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int ee = e0 + j - half * TP;
+          const int e = e0 + j, en = SINGLE ? net : e / TP, ee = SINGLE ? e : e - en * TP;
           float v = 0.0f;
-          if (valid && half == net && ee < a.nT) v = w2[ee * lw.Ks2 + unit];
+          if (valid && en == net && ee < a.nT) v = w2[ee * lw.Ks2 + unit];
           hi[j] = __float_as_uint(v);
           lo[j] = __float_as_uint(lo_part(v));
         }
@@ -450,21 +475,21 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
           for (int j0 = 0; j0 < NU; j0 += 16) {
             uint32_t vm[16], vc[16];
             tmem_ld_x16(trow + ACC1 + j0, vm);
-            tmem_ld_x16(trow + ACC1 + NU + j0, vc);
+            if (MERGED) tmem_ld_x16(trow + ACC1 + NU + j0, vc);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum[j0 + j] += __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+            for (int j = 0; j < 16; ++j) sum[j0 + j] += MERGED ? __uint_as_float(vm[j]) + __uint_as_float(vc[j]) : __uint_as_float(vm[j]);
           }
         } else {
-          const uint32_t acc = trow + ACC2 + net * 2 * TP;
+          const uint32_t acc = trow + ACC2 + (MERGED ? net * 2 * TP : 0);
 #pragma unroll
           for (int j0 = 0; j0 < TP; j0 += 16) {
             uint32_t vm[16], vc[16];
             tmem_ld_x16(acc + j0, vm);
-            tmem_ld_x16(acc + TP + j0, vc);
+            if (MERGED) tmem_ld_x16(acc + TP + j0, vc);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum[j0 + j] += __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+            for (int j = 0; j < 16; ++j) sum[j0 + j] += MERGED ? __uint_as_float(vm[j]) + __uint_as_float(vc[j]) : __uint_as_float(vm[j]);
           }
         }
         fence_before_sync();
@@ -495,22 +520,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __gr
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
-template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT>
+template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT, bool SINGLE = false>
 cudaError_t launch_tc(const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
   if (a.K1P8 != K1P8) return cudaErrorInvalidValue;
-  auto k = rnvp_wgrad_tc_kernel<NU, K1P8, TP, NBUF, NOP, NSLOT>;
-  const size_t smem = rnvp_wgrad_tc_smem_bytes(NU, TP, NBUF, NOP, NSLOT, a.K1P8);
+  auto k = rnvp_wgrad_tc_kernel<NU, K1P8, TP, NBUF, NOP, NSLOT, SINGLE>;
+  const size_t smem = rnvp_wgrad_tc_smem_bytes(NU, TP, NBUF, NOP, NSLOT, a.K1P8, SINGLE ? 1 : 2);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<grid, WT_THREADS, smem, st>>>(a);
+  k<<<grid, SINGLE ? 384 : WT_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, int K1P8) {
-  const size_t raw = (size_t)WT_ROWS * (128 + K1P8 + 2 * TP);
-  const size_t opf = 2 * (size_t)(NU / 8) * WT_NG + 4 * (size_t)(TP / 8) * WT_NG + 2 * (size_t)WT_ROWS * 2 * TP;
+size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, int K1P8, int NN) {
+  const size_t raw = (size_t)WT_ROWS * (128 + K1P8 + NN * TP);
+  const size_t opf = 2 * (size_t)(NU / 8) * WT_NG + 2 * NN * (size_t)(TP / 8) * WT_NG + 2 * (size_t)WT_ROWS * NN * TP;
   return (NSLOT * raw + NOP * opf) * 4 + 8 * (2 * NSLOT + 2 * NOP + 3 * NBUF + 2) + 64;
 }
 
@@ -525,6 +550,8 @@ cudaError_t rnvp_launch_wgrad_tc(int NU, int TP, const RnvpWgradTcArgs& a, int g
     return launch_tc<32, 24, 16, 2, 4, 4>(a, grid, st);
   }
   if (NU == 32 && TP == 16 && a.K1P8 == 16) return launch_tc<32, 16, 16, 2, 4, 4>(a, grid, st);
-  if (NU == 48 && TP == 32 && a.K1P8 == 48) return launch_tc<48, 48, 32, 1, 3, 4>(a, grid, st);
+  if (NU == 48 && TP == 32 && a.K1P8 == 48) return launch_tc<48, 48, 32, 1, 2, 3>(a, grid, st);
+  // wide flows (rnvp_wide.cu fit sweeps): D = 128 (c5: K1P8 = 96, TP = 64), single-net lane blocks
+  if (NU == 96 && TP == 64 && a.K1P8 == 96 && a.H % 128 == 0) return launch_tc<96, 96, 64, 1, 2, 2, true>(a, grid, st);
   return cudaErrorInvalidValue;
 }

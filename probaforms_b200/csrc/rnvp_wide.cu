@@ -174,9 +174,32 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(tbase + D2C, ah + 8 * j, desc(w2 + 16u * j, hi2), idesc2m, 1u);
     };
+    // backward sweep (MODE 2).  gemmA: dh chunk = delta2_net W2_net[:, chunk]  (A = delta2 hi / lo in TMEM, B = W2T chunk image
+    // [CU units x NTP]); gemmB: [DUM | DUC] += delta1 x [W1T_hi ; W1T_lo], DUC += delta1_lo x W1T_hi (B = W1T chunk image
+    // [NTP x CU], the same shape as the forward W2 chunk)
+    const uint32_t hiT = ((uint32_t)(NTP >> 2) * 128u >> 4) | (1u << 14);       // SBO of the W2T chunk image (K = NTP)
+    auto gemmA = [&](int st, int buf, int net) {
+      const uint32_t bh = sm_lo + (uint32_t)st * stage16, bl = bh + ((uint32_t)(CU * NTP) * 4u >> 4);
+      const uint32_t d = tbase + DHB + buf * 2 * CU;
+      const uint32_t eh = tbase + E2H + net * DH, el = tbase + E2L + net * DH;
+#pragma unroll
+      for (int j = 0; j < DH / 8; ++j) mma_tf32_ts(d, el + 8 * j, desc(bh + 16u * j, hiT), idesc1, j ? 1u : 0u);
+#pragma unroll
+      for (int j = 0; j < DH / 8; ++j) mma_tf32_ts(d, eh + 8 * j, desc(bl + 16u * j, hiT), idesc1, 1u);
+#pragma unroll
+      for (int j = 0; j < DH / 8; ++j) mma_tf32_ts(d, eh + 8 * j, desc(bh + 16u * j, hiT), idesc1, 1u);
+    };
+    auto gemmB = [&](int st, int buf, int cc) {
+      const uint32_t w1t = sm_lo + (uint32_t)st * stage16 + ((uint32_t)W2C * 4u >> 4);
+      const uint32_t ah = tbase + DHB + buf * 2 * CU, al = ah + CU;
+#pragma unroll
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(tbase + DUM, ah + 8 * j, desc(w1t + 16u * j, hi2), idesc2m, (cc | j) ? 1u : 0u);
+#pragma unroll
+      for (int j = 0; j < CU / 8; ++j) mma_tf32_ts(tbase + DUC, al + 8 * j, desc(w1t + 16u * j, hi2), idesc2, 1u);
+    };
     uint32_t ph_u = 0, ph_a = 0, ph_w = 0;              // ph_a / ph_w: one bit per buffer / stage
     long long step = 0;
-    for (int it = 0; it < my_tiles; ++it)
+    for (int it = 0; it < my_tiles; ++it) {
       for (int li = 0; li < nL; ++li) {
         mbar_wait(&bars[WB_UF], ph_u); ph_u ^= 1;
         {
@@ -206,6 +229,37 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
           __syncwarp();
         }
       }
+      if (do_bwd) {
+        for (int li = 0; li < nL; ++li) {
+          mbar_wait(&bars[WB_UF], ph_u); ph_u ^= 1;           // delta2 of the layer staged in TMEM
+          {
+            const int st = (int)(step % WD_STAGES);
+            mbar_wait(&bars[WB_WF + st], (ph_w >> st) & 1u); ph_w ^= 1u << st;
+            fence_after_sync();
+            if (leader) { gemmA(st, 0, 0); mma_commit(&bars[WB_D1F0]); }
+            __syncwarp();
+          }
+          for (int cc = 0; cc < NCS; ++cc, ++step) {
+            const int st = (int)(step % WD_STAGES), buf = cc & 1;
+            if (cc + 1 < NCS) {
+              const int st1 = (int)((step + 1) % WD_STAGES);
+              mbar_wait(&bars[WB_WF + st1], (ph_w >> st1) & 1u); ph_w ^= 1u << st1;
+              fence_after_sync();
+              if (leader) { gemmA(st1, buf ^ 1, (cc + 1) >= NC ? 1 : 0); mma_commit(&bars[WB_D1F0 + (buf ^ 1)]); }
+              __syncwarp();
+            }
+            mbar_wait(&bars[WB_AF0 + buf], (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+            fence_after_sync();
+            if (leader) {
+              gemmB(st, buf, cc);
+              mma_commit(&bars[WB_WE + st]);
+              if (cc + 1 == NCS) mma_commit(&bars[WB_D2F]);       // du of the layer complete
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: two threads per row
     const int quarter = warp & 3, half = (warp - 4) >> 2;
@@ -226,6 +280,20 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
         else if (valid) v = __ldg(reinterpret_cast<const float4*>(a.X + src * D + half * DH) + m);
         xa[2 * m] = v.x; xb[2 * m] = v.y; xa[2 * m + 1] = v.z; xb[2 * m + 1] = v.w;
       }
+      // activation records of (layer i, this row): [layer][block of 32 rows][column group of 4][32 slots][4 floats], slot =
+      // (row % 32) ^ (group & 7) (rnvp_wgrad_tc.cu): a warp-level float4 access covers 512 contiguous bytes
+      const int K1P8 = (DH + Cd + 7) & ~7;
+      auto rec_base = [&](int i) -> float* {
+        return a.records + (((size_t)i * (size_t)(a.Npad >> 5) + (size_t)(row >> 5)) * (size_t)(a.rec >> 2)) * 128;
+      };
+      auto rec_st = [&](float* rb, int col, float4 v) {
+        const int cg = col >> 2;
+        *reinterpret_cast<float4*>(rb + cg * 128 + ((lane ^ (cg & 7)) << 2)) = v;
+      };
+      // forward stash of this kernel's own backward sweep: [block of 32 rows][layer][float4 group (2 DH / 4)][32 rows][4]
+      auto stash_ptr = [&](int i, int group) -> float* {
+        return a.stash + (((size_t)(row >> 5) * a.L_total + i) * (2 * DH / 4) + group) * 128 + lane * 4;
+      };
       // static part of u: [c | 1 | 0...] at columns DH.. of U_HI / U_LO, written once per tile; the 8-column pieces are
       // shared out between the two threads of the row
 #pragma unroll
@@ -242,10 +310,22 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
           }
           tmem_st_x8(trow + U_HI + DH + e0, hi);
           tmem_st_x8(trow + U_LO + DH + e0, lo);
+          if (MODE == 2 && do_bwd && DH + e0 < K1P8) {
+            // the condition part of u = [x_K, c] is the same for every layer: written into all records of the row now
+            float4 c0, c1;
+            c0.x = (e0 + 0 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 0) : 0.f; c0.y = (e0 + 1 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 1) : 0.f;
+            c0.z = (e0 + 2 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 2) : 0.f; c0.w = (e0 + 3 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 3) : 0.f;
+            c1.x = (e0 + 4 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 4) : 0.f; c1.y = (e0 + 5 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 5) : 0.f;
+            c1.z = (e0 + 6 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 6) : 0.f; c1.w = (e0 + 7 < Cd && valid) ? __ldg(a.C + src * Cd + e0 + 7) : 0.f;
+            for (int i = a.l0; i < a.l1; ++i) {
+              rec_st(rec_base(i), 2 * H + DH + e0, c0);
+              rec_st(rec_base(i), 2 * H + DH + e0 + 4, c1);
+            }
+          }
         }
       }
 
-      auto layer = [&](float (&xT)[HALF], float (&xK)[HALF]) {
+      auto layer = [&](float (&xT)[HALF], float (&xK)[HALF], int i) {
         // ---- this thread's half of the conditioning features -> u (hi / lo) in TMEM
 #pragma unroll
         for (int e0 = 0; e0 < HALF; e0 += 8) {
@@ -258,6 +338,12 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
         tmem_wait_st();
         fence_before_sync();
         mbar_arrive(&bars[WB_UF]);
+        if (MODE == 2 && do_bwd) {               // x_K half of u -> record (the weight-gradient sweep contracts it with delta1)
+          float* rb = rec_base(i);
+#pragma unroll
+          for (int m = 0; m < HALF / 4; ++m)
+            rec_st(rb, 2 * H + half * HALF + 4 * m, make_float4(xK[4 * m], xK[4 * m + 1], xK[4 * m + 2], xK[4 * m + 3]));
+        }
         float tpark[HALF];
         for (int cc = 0; cc < NCS; ++cc) {
           const int buf = cc & 1;
@@ -270,7 +356,20 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
             tmem_ld_x16(d1, r);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_tf32(act_wide<ACT>(__uint_as_float(r[j])), r[j], lo[j]);
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(act_wide<ACT>(__uint_as_float(r[j])));
+            if (MODE == 2 && do_bwd) {
+              // h goes to the activation record now: the backward sweep and the weight-gradient sweep read it back.  Chunk
+              // step cc holds units (cc % NC) * CU .. of net cc / NC; this thread has columns 16 * half .. of the chunk
+              const int net = cc >= NC ? 1 : 0;
+              float* rb = rec_base(i);
+              const int col0 = net * H + (cc - net * NC) * CU + 16 * half;
+#pragma unroll
+              for (int m = 0; m < 4; ++m)
+                rec_st(rb, col0 + 4 * m, make_float4(__uint_as_float(r[4 * m]), __uint_as_float(r[4 * m + 1]),
+                                                     __uint_as_float(r[4 * m + 2]), __uint_as_float(r[4 * m + 3])));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_tf32(__uint_as_float(r[j]), r[j], lo[j]);
             tmem_st_x16(d1, r);
             tmem_st_x16(d1 + CU, lo);
           }
@@ -305,16 +404,28 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
           for (int j = 0; j < 16; ++j) {
             const float s = __uint_as_float(sv[j]) + __uint_as_float(sc[j]);
             const float t = tpark[e0 + j];
+            if (MODE == 2) { sv[j] = __float_as_uint(s); sc[j] = __float_as_uint(xT[e0 + j]); }      // stash s and x_T
             if (MODE != 1) { xT[e0 + j] = fmaf(xT[e0 + j], exp_wide(s), t); ld += s; }
             else xT[e0 + j] = (xT[e0 + j] - t) * exp_wide(-s);
+          }
+          if (MODE == 2 && do_bwd) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              *reinterpret_cast<float4*>(stash_ptr(i, (half * HALF + e0) / 4 + m)) =
+                  make_float4(__uint_as_float(sc[4 * m]), __uint_as_float(sc[4 * m + 1]), __uint_as_float(sc[4 * m + 2]),
+                              __uint_as_float(sc[4 * m + 3]));
+              *reinterpret_cast<float4*>(stash_ptr(i, DH / 4 + (half * HALF + e0) / 4 + m)) =
+                  make_float4(__uint_as_float(sv[4 * m]), __uint_as_float(sv[4 * m + 1]), __uint_as_float(sv[4 * m + 2]),
+                              __uint_as_float(sv[4 * m + 3]));
+            }
           }
         }
         fence_before_sync();                     // the next layer's first GEMM2 (after the next a_full) overwrites D2 / C2
       };
       for (int li = 0; li < nL; ++li) {
         const int i = MODE != 1 ? a.l0 + li : a.l1 - 1 - li;
-        if ((i & 1) == 0) layer(xa, xb);                 // even layer transforms the even features
-        else layer(xb, xa);
+        if ((i & 1) == 0) layer(xa, xb, i);              // even layer transforms the even features
+        else layer(xb, xa, i);
       }
 
       if (valid && a.out_x) {
@@ -329,12 +440,121 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
         // the second thread of the row hands its partial sums to the first
         if (half == 1) { xch[2 * rin] = ld; xch[2 * rin + 1] = q; }
         asm volatile("bar.sync 2, 256;" ::: "memory");
+        float lp = 0.0f;
         if (half == 0 && valid) {
           const float ldt = ld + xch[2 * rin], qt = q + xch[2 * rin + 1];
+          lp = ldt - 0.5f * (D * 1.8378770664093453f + qt);
           if (a.out_logdet) a.out_logdet[row] = ldt;
-          if (a.out_logp) a.out_logp[row] = ldt - 0.5f * (D * 1.8378770664093453f + qt);
+          if (a.out_logp) a.out_logp[row] = lp;
+        }
+        if (MODE == 2 && a.loss_sum && half == 0) {
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, m);
+          if (lane == 0) atomicAdd(a.loss_sum, lp);
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");   // xch is reused by the next tile
+      }
+
+      // ================================================================ backward sweep (fit step)
+      if constexpr (MODE == 2) {
+        if (do_bwd) {
+          // gradient of scale * sum_rows logp w.r.t. the current activations: g_z = -scale * z, g_logdet = scale
+          const float gld = valid ? a.scale : 0.0f;
+          float ga[HALF], gb[HALF];
+#pragma unroll
+          for (int e = 0; e < HALF; ++e) { ga[e] = -gld * xa[e]; gb[e] = -gld * xb[e]; }
+          auto layer_bwd = [&](float (&gT)[HALF], float (&gK)[HALF], int i) {
+            float* rb = rec_base(i);
+            if (i > a.l0) {       // the next layer's stash block of this thread's rows: pull it into L2 now
+#pragma unroll
+              for (int m = 0; m < HALF / 4; ++m) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(stash_ptr(i - 1, half * HALF / 4 + m)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(stash_ptr(i - 1, DH / 4 + half * HALF / 4 + m)));
+              }
+            }
+            // ---- x_T and s of this layer from the forward stash; delta2 (hi / lo) -> TMEM and -> record; new g_T
+#pragma unroll
+            for (int e0 = 0; e0 < HALF; e0 += 8) {
+              uint32_t th[8], tl[8], sh[8], sl[8];
+              float d2t[8], d2s[8];
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                const float4 xv = *reinterpret_cast<const float4*>(stash_ptr(i, (half * HALF + e0) / 4 + m));
+                const float4 sv = *reinterpret_cast<const float4*>(stash_ptr(i, DH / 4 + (half * HALF + e0) / 4 + m));
+                const float xs4[4] = {xv.x, xv.y, xv.z, xv.w}, ss4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) {
+                  const int e = e0 + 4 * m + q2;
+                  const float es = exp_wide(ss4[q2]);
+                  d2t[4 * m + q2] = gT[e];                                   // dL/dt
+                  d2s[4 * m + q2] = fmaf(gT[e] * xs4[q2], es, gld);          // dL/ds = g_y * x * exp(s) + g_logdet
+                  gT[e] *= es;                                               // dL/dx_T
+                  split_tf32(d2t[4 * m + q2], th[4 * m + q2], tl[4 * m + q2]);
+                  split_tf32(d2s[4 * m + q2], sh[4 * m + q2], sl[4 * m + q2]);
+                }
+              }
+              tmem_st_x8(trow + E2H + half * HALF + e0, th);
+              tmem_st_x8(trow + E2L + half * HALF + e0, tl);
+              tmem_st_x8(trow + E2H + DH + half * HALF + e0, sh);
+              tmem_st_x8(trow + E2L + DH + half * HALF + e0, sl);
+              rec_st(rb, 2 * H + K1P8 + half * HALF + e0, make_float4(d2t[0], d2t[1], d2t[2], d2t[3]));
+              rec_st(rb, 2 * H + K1P8 + half * HALF + e0 + 4, make_float4(d2t[4], d2t[5], d2t[6], d2t[7]));
+              rec_st(rb, 2 * H + K1P8 + DH + half * HALF + e0, make_float4(d2s[0], d2s[1], d2s[2], d2s[3]));
+              rec_st(rb, 2 * H + K1P8 + DH + half * HALF + e0 + 4, make_float4(d2s[4], d2s[5], d2s[6], d2s[7]));
+            }
+            tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive(&bars[WB_UF]);
+            // ---- chunk steps: delta1 = dh * act'(h), dh from the tensor core, h from the record the forward sweep wrote
+            for (int cc = 0; cc < NCS; ++cc) {
+              const int buf = cc & 1, net = cc >= NC ? 1 : 0;
+              const int col0 = net * H + (cc - net * NC) * CU + 16 * half;
+              uint32_t hv[16];
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {           // issued before the wait for dh: the L2 / HBM latency hides behind the MMAs
+                const int cg = (col0 >> 2) + m;
+                const float4 v = *reinterpret_cast<const float4*>(rb + cg * 128 + ((lane ^ (cg & 7)) << 2));
+                hv[4 * m] = __float_as_uint(v.x); hv[4 * m + 1] = __float_as_uint(v.y);
+                hv[4 * m + 2] = __float_as_uint(v.z); hv[4 * m + 3] = __float_as_uint(v.w);
+              }
+              mbar_wait(&bars[WB_D1F0 + buf], (ph_d1 >> buf) & 1u); ph_d1 ^= 1u << buf;
+              fence_after_sync();
+              const uint32_t d1 = trow + DHB + buf * 2 * CU + 16 * half;
+              uint32_t dh[16], lo[16];
+              tmem_ld_x16(d1, dh);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float h = __uint_as_float(hv[j]);
+                const float dp = ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f);
+                split_tf32(__uint_as_float(dh[j]) * dp, dh[j], lo[j]);
+              }
+              tmem_st_x16(d1, dh);
+              tmem_st_x16(d1 + CU, lo);
+              tmem_wait_st();
+              fence_before_sync();
+              mbar_arrive(&bars[WB_AF0 + buf]);
+            }
+            // ---- du -> g_x_K (this thread's half of the conditioning features)
+            mbar_wait(&bars[WB_D2F], ph_d2); ph_d2 ^= 1;
+            fence_after_sync();
+#pragma unroll
+            for (int e0 = 0; e0 < HALF; e0 += 16) {
+              uint32_t um[16], uc[16];
+              tmem_ld_x16(trow + DUM + half * HALF + e0, um);
+              tmem_ld_x16(trow + DUC + half * HALF + e0, uc);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) gK[e0 + j] += __uint_as_float(um[j]) + __uint_as_float(uc[j]);
+            }
+            fence_before_sync();
+          };
+          for (int li = 0; li < nL; ++li) {
+            const int i = a.l1 - 1 - li;
+            if ((i & 1) == 0) layer_bwd(ga, gb, i);
+            else layer_bwd(gb, ga, i);
+          }
+        }
       }
     }
   }
@@ -355,8 +575,10 @@ cudaError_t launch_wide_shape(int act, int mode, const RnvpMmaArgs& a, int grid,
   }
   if (act == 1 && mode == 0) RNVP_WIDE_LAUNCH(1, 0)
   if (act == 1 && mode == 1) RNVP_WIDE_LAUNCH(1, 1)
+  if (act == 1 && mode == 2) RNVP_WIDE_LAUNCH(1, 2)
   if (act == 2 && mode == 0) RNVP_WIDE_LAUNCH(2, 0)
   if (act == 2 && mode == 1) RNVP_WIDE_LAUNCH(2, 1)
+  if (act == 2 && mode == 2) RNVP_WIDE_LAUNCH(2, 2)
 #undef RNVP_WIDE_LAUNCH
   return cudaErrorInvalidValue;
 }

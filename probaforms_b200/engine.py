@@ -83,10 +83,10 @@ class FlowEngine:
 
     @property
     def fit_on_tensor_cores(self):
-        """True when rnvp_backward runs rnvp_mma_kernel<..,2> (tcgen05 forward + backward sweeps) followed by
-        rnvp_wgrad_kernel: tcgen05-eligible flows with D = 32 and one hidden layer of width <= 128 (multiple of 16)."""
-        return (self._bwd_two_kernels and self.D == 32 and len(self.hidden) == 1 and self.hidden[0] <= 128
-                and self.hidden[0] % 16 == 0)
+        """True when rnvp_backward runs entirely on the tensor cores: tcgen05 forward + backward sweeps (rnvp_mma_kernel<..,2> for
+        D = 32 flows with H <= 128, rnvp_wide_kernel<..,2> for wide flows with H a multiple of 128) followed by
+        rnvp_wgrad_tc_kernel (plan_info pseudo-mode 4)."""
+        return self.plan_info(4)["kernel_family"] == 2
 
     def __del__(self):
         try:

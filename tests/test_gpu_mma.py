@@ -92,8 +92,9 @@ def test_fit_steps_on_tcgen05_path_track_fp32_path():
     assert torch.allclose(curves[0], curves[1], rtol=1e-4, atol=1e-4), (curves[0], curves[1])
 
 
-@pytest.mark.parametrize("H,N", [(64, 2048), (128, 4096 + 32), (96, 960), (32, 64)])
-def test_wgrad_sweep_through_the_abi_matches_fp64(H, N):
+@pytest.mark.parametrize("D,Cd,H,N", [(32, 8, 64, 2048), (32, 8, 128, 4096 + 32), (32, 8, 96, 960), (32, 8, 32, 64),
+                                      (64, 16, 128, 2048), (128, 32, 128, 1024), (128, 32, 512, 4096)])
+def test_wgrad_sweep_through_the_abi_matches_fp64(D, Cd, H, N):
     """rnvp_wgrad_sweep alone (C ABI): blocked records [L][N/32][rec/4][32][4] built on the host side of the ABI, gradients
     against an fp64 evaluation of dW1 = delta1^T u, dW2 = delta2^T h with delta1 = (delta2 W2) * (1 - h^2).  H = 64 puts
     both nets into one 128-lane block (block-diagonal W2 image), H = 128 gives one block per net, H = 48 / 16 partial blocks."""
@@ -101,7 +102,7 @@ def test_wgrad_sweep_through_the_abi_matches_fp64(H, N):
     from probaforms_b200 import _lib
     from probaforms_b200.models import RealNVPLayer, NormalizingFlow
     dev = torch.device("cuda:0")
-    D, Cd, L = 32, 8, 3
+    L = 3
     K1P = (D // 2 + Cd + 7) // 8 * 8
     torch.manual_seed(0)
     nf = NormalizingFlow([RealNVPLayer(D, Cd, (torch.arange(D) + i) % 2, (H,), "tanh") for i in range(L)], None).to(dev)
