@@ -435,14 +435,20 @@ def main():
                       "log_prob_algorithmic_tflops": o_lp / world * fo_fwd / 1e12}
                 if fam_o.startswith("tcgen05"):
                     e1["log_prob_executed_tf32_tflops"] = 3 * o_lp / world * fo_fwd / 1e12
-                if name == "c5":
+                if name == "c5" or path == 0:
                     engo.zero_grads()
                     r_fit, ms_fit = time_pass(lambda: engo.backward(Xo, Co, None, per_o, -1.0 / per_o), per_o, reps=3)
                     engo.zero_grads()
                     e1.update({"fit_kernel_rows_s": r_fit, "fit_rows_per_launch": per_o, "fit_ms": ms_fit,
                                "fit_algorithmic_tflops": r_fit / world * fo_fit / 1e12,
-                               "fit_kernels": ("rnvp_tile_kernel<TR,2> (FP32-FMA fused forward+backward)"
-                                               if engo.plan_info(2)["kernel_family"] != 2 else "tensor-core forward sweep + FP32 backward sweep")})
+                               "fit_kernels": ("rnvp_wide_kernel<64,32,32,1,2> (tcgen05 streamed forward + backward sweeps) + "
+                                               "rnvp_wgrad_tc_kernel<96,96,64,..,single-net> (tcgen05 weight-gradient sweep)"
+                                               if engo.fit_on_tensor_cores and name == "c5" else
+                                               "rnvp_wide_kernel<32,16,32,1,2> + rnvp_wgrad_tc_kernel<48,48,32,..> (tcgen05)"
+                                               if engo.fit_on_tensor_cores else
+                                               "rnvp_tile_kernel<TR,2> (FP32-FMA fused forward+backward)")})
+                    if engo.fit_on_tensor_cores:
+                        e1["fit_executed_tf32_tflops"] = 3 * r_fit / world * fo_fit / 1e12
                 ent[tag] = e1
             engo.set_path(0)
             if name == "c5":

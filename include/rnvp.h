@@ -11,8 +11,13 @@
  *    contiguous fp32 (or int64 where stated) memory owned by the caller (torch);
  *    the library never allocates or frees caller-visible memory.  The opaque
  *    descriptor owns a few KB of device tables (its per-tile op programs).
- *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no
- *    entry point synchronises, so calls are CUDA-graph capturable.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.  The per-tile programs of the
+ *    FP32 kernels for the whole flow are built and uploaded by rnvp_desc_create (synchronous, once), so
+ *    rnvp_forward / rnvp_inverse / rnvp_sample / rnvp_backward / rnvp_adam_step over the full layer range
+ *    neither allocate nor synchronise and are CUDA-graph capturable; a call on a layer SUB-range
+ *    (RealNVPLayer.f / .g) builds its program on first use (one cudaMalloc + synchronous copy, then cached).
+ *  - the only process-global mutable state is the development trace pointer of rnvp_debug_set_trace;
+ *    everything else lives in the descriptor (guarded by a mutex) or on the caller's stream.
  *  - every function returns 0 on success, a negative RNVP_E* code for argument /
  *    planning errors, or a positive cudaError_t.  rnvp_last_error() returns a
  *    thread-local message.  Nothing throws, exits, or falls back to the CPU.
@@ -56,8 +61,8 @@ int64_t rnvp_param_count(const rnvp_desc* d);    /* P: flat reference-layout par
 int64_t rnvp_packed_count(const rnvp_desc* d);   /* kernel-private packed layouts (all kernel families) */
 int64_t rnvp_grad_count(const rnvp_desc* d);     /* floats of the packed gradient accumulator d_gpacked */
 /* bytes of scratch rnvp_backward needs for a batch of N rows: the per-CTA x_T stash of the fused FP32 kernel
- * (independent of N, stays L2 resident) or, on the tcgen05 path, z plus the per-layer (x_T, s) stash of the
- * tensor-core forward sweep, N*(D + L*D)*4 bytes */
+ * (independent of N, stays L2 resident); on the tensor-core fit paths the per-layer (x_T, s) stash plus the
+ * activation records, Npad*L*(D + rnvp_wgrad_record_floats)*4 bytes (Npad = N rounded up to whole row tiles) */
 int64_t rnvp_workspace_bytes(const rnvp_desc* d, int64_t N);
 /* offsets[2*k], offsets[2*k+1] = (float offset, numel) of the k-th tensor of nf.parameters();
  * n = 4*(n_hidden+1)*L entries pairs.  Returns the number of tensors. */
@@ -96,9 +101,13 @@ int rnvp_sample(const rnvp_desc* d, const float* d_packed, const float* d_C, int
                 int64_t row_offset, float* d_X, void* stream);
 
 /* Fused forward + backward of  out = scale * sum_rows logp(row)  (loss.backward() of
- * loss = -nf.log_prob(X, C), realnvp.py:246-250, is scale = -1/N).  Activations are recomputed,
- * weight gradients are ACCUMULATED into d_gpacked (caller zeroes it), sum_rows logp is
- * accumulated into d_logp_sum (1 float, may be NULL), per-row logp optionally written. */
+ * loss = -nf.log_prob(X, C), realnvp.py:246-250, is scale = -1/N).  Weight gradients are ACCUMULATED into
+ * d_gpacked (caller zeroes it), sum_rows logp is accumulated into d_logp_sum (1 float, may be NULL), per-row
+ * logp optionally written.  Kernel families: small flows and the generic FP32 tile kernel recompute the
+ * hidden activations in the backward sweep (nothing but x_T per layer is kept); the tensor-core fit paths
+ * (D = 32 flows with H <= 128; D = 64 / 128 flows with H a multiple of 128) hand h, u and delta2 of every
+ * (layer, row) to the weight-gradient sweep through activation records in d_workspace (see
+ * rnvp_wgrad_sweep), which is why rnvp_workspace_bytes grows with N there. */
 int rnvp_backward(const rnvp_desc* d, const float* d_packed, const float* d_X, const float* d_C,
                   const int64_t* d_idx, int64_t N, float scale, float* d_gpacked, float* d_logp_sum,
                   float* d_logp, void* d_workspace, int64_t workspace_bytes, void* stream);
@@ -125,7 +134,8 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
  * h [2][H] (nn_t | nn_s) | u = [x_K, c, 0..] (ceil8(D/2+Cd)) | delta2 [2][D/2],
  * stored in blocks of 32 rows as d_records[L][Npad/32][rec/4][32][4]: float4 column group q of row r of a block sits
  * in slot (r ^ (q & 7)).  Npad is a multiple of 32; padding rows must hold zeros in delta1 / delta2.
- * tcgen05-eligible flows with D = 32, H <= 128. */
+ * Flows whose fit step runs on the tensor cores: D = 32 with H <= 128 (multiple of 16), D = 64 / 128 with H a
+ * multiple of 128 (one 128-lane block of hidden units per CTA, rnvp_wgrad_tc.cu). */
 int rnvp_wgrad_record_floats(const rnvp_desc* d);
 int rnvp_wgrad_sweep(const rnvp_desc* d, const float* d_packed, int64_t Npad, const float* d_records, float* d_gpacked,
                      void* stream);

@@ -30,8 +30,6 @@ int rnvp_small_fit_rows_per_block();
 int rnvp_small_fit_max_layers();
 cudaError_t rnvp_launch_mma(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, size_t smem, cudaStream_t st);
 size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats, int w1t_floats);
-cudaError_t rnvp_launch_wgrad(int NT1, int NT2, const RnvpWgradArgs& a, int grid, size_t smem, cudaStream_t st);
-size_t rnvp_wgrad_smem_bytes(int rec, int bw);
 cudaError_t rnvp_launch_wgrad_tc(int NU, int TP, const RnvpWgradTcArgs& a, int grid, cudaStream_t st);
 cudaError_t rnvp_launch_wide(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, cudaStream_t st);
 cudaError_t rnvp_launch_mma_selftest(const float* A, const float* B, float* D, int N, int K, int passes, cudaStream_t st);
@@ -71,7 +69,6 @@ struct rnvp_desc : rnvp_planner::FlowGeom {
   int* d_f2m = nullptr;   // [4*P]: positions of each parameter's TF32 hi / lo images (plain, transposed) in the tcgen05 region, or -1
   RnvpWgradLayer* d_wg = nullptr;   // per-layer gradient offsets for the weight-gradient sweep
   int path = 0;           // 0 auto, 1 FP32 tile/small kernels only, 2 tcgen05 where eligible
-  int wgrad_legacy = 0;   // development knob (env RNVP_WGRAD=legacy at descriptor creation): mma.sync weight-gradient sweep
   std::map<std::tuple<int, int, int>, Program> programs;
   std::mutex mu;
 };
@@ -287,7 +284,7 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.layer_floats = d->m_layer_floats; a.w1_floats = d->m_w1_floats; a.w2_floats = d->m_w2_floats;
   a.stash = stash; a.loss_sum = loss_sum; a.L_total = d->L;
   a.do_bwd = records != nullptr; a.scale = scale; a.records = records; a.rec = 0; a.Npad = 0;
-  a.rec_swz = d->wgrad_legacy ? 1 : 7;
+  a.rec_swz = 7;
   a.wt_floats = records ? d->m_wt_floats : 0;
   a.trace = g_mma_trace;
   a.seed = seed; a.row_offset = row_offset;
@@ -344,7 +341,6 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
   d->device = dev;
   d->num_sms = prop.multiProcessorCount;
   d->max_smem = (int)prop.sharedMemPerBlockOptin;
-  { const char* w = getenv("RNVP_WGRAD"); d->wgrad_legacy = (w && !strcmp(w, "legacy")) ? 1 : 0; }
   build_layout(d);
   if (d->P >= 0x7fffffffLL) { delete d; return fail(RNVP_ESHAPE, "flow too large (>= 2^31 parameters)"); }
   std::vector<int> p2f, f2p, f2p2;
@@ -396,6 +392,13 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
   if (e == cudaSuccess) e = cudaMemcpy(d->d_p2f, p2f.data(), sizeof(int) * p2f.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d->d_f2p, f2p.data(), sizeof(int) * f2p.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { rnvp_desc_destroy(d); return cuda_fail(e, "descriptor tables"); }
+  // programs of the FP32 kernels over the full layer range: built now, so that the hot entry points never allocate
+  // (shapes the tile planner cannot fit are reported when such a program is actually needed)
+  {
+    Program* p = nullptr;
+    for (int mode = 0; mode <= 3; ++mode) get_program(d, mode, 0, d->L, &p);
+    g_err.clear();
+  }
   *out = d;
   return 0;
 }
@@ -631,7 +634,7 @@ int rnvp_wgrad_sweep(const rnvp_desc* dc, const float* d_packed, int64_t Npad, c
   if (!d_records || !d_gpacked || !d_packed) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: null buffer");
   if (Npad <= 0 || Npad % 32) return fail(RNVP_EINVAL, "rnvp_wgrad_sweep: Npad must be a positive multiple of 32");
   const int K1P = (d->mDH + d->Cd + 7) & ~7, TP = d->mDH;
-  if (!d->wgrad_legacy || d->m_netseq) {
+  {
     // tcgen05 sweep: one CTA per (layer, block of 128 hidden units of [nn_t | nn_s], row slice), one wave of CTAs
     RnvpWgradTcArgs a;
     a.gR = d_records; a.rec = wgrad_rec_floats(d); a.Npad = Npad; a.H = d->hidden[0];
@@ -644,13 +647,6 @@ int rnvp_wgrad_sweep(const rnvp_desc* dc, const float* d_packed, int64_t Npad, c
     cudaError_t e = rnvp_launch_wgrad_tc(NU, TP, a, d->L * a.n_mblocks * a.n_slices, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "rnvp_wgrad_tc_kernel");
   }
-  RnvpWgradArgs a;
-  a.gR = d_records; a.rec = wgrad_rec_floats(d); a.gpacked = d_gpacked; a.layers = d->d_wg;
-  a.packed = d_packed; a.act = d->act;
-  a.Npad = Npad; a.H = d->hidden[0];
-  a.n_slices = (int)std::max<long long>(1, std::min<long long>(Npad / 32, d->num_sms / d->L));   // one wave of CTAs
-  cudaError_t e = rnvp_launch_wgrad(K1P / 8, TP / 8, a, d->L * a.n_slices, rnvp_wgrad_smem_bytes(a.rec, K1P + 2 * TP), (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "rnvp_wgrad_kernel");
 }
 
 int rnvp_debug_set_trace(void* d_buf) { g_mma_trace = (long long*)d_buf; return 0; }

@@ -1,4 +1,4 @@
-// Arguments of the weight-gradient sweep kernel (rnvp_wgrad.cu).
+// Arguments of the weight-gradient sweep kernel (rnvp_wgrad_tc.cu).
 #pragma once
 #include <stdint.h>
 
@@ -6,18 +6,6 @@ struct RnvpWgradLayer {            // where one layer's gradients live in the pa
   int w1_off[2], b1_off[2];        // first Linear of nn_t / nn_s: rows = hidden units, row stride Ks1
   int w2_off[2], b2_off[2];        // last Linear: rows = transformed features, row stride Ks2
   int Ks1, Ks2;
-};
-
-struct RnvpWgradArgs {
-  const float* gR;                 // records [L][Npad/32][rec/4][32][4]: h (2H) | u (K1P) | delta2 (2*TP)
-  int rec;                         // floats per record (multiple of 8)
-  float* gpacked;
-  const float* packed;             // packed parameters (tile layout, same offsets as gpacked): W2 for the delta1 recompute
-  int act;                         // 1 tanh, 2 relu
-  const RnvpWgradLayer* layers;    // device array, L entries
-  long long Npad;                  // rows, multiple of 32; padding rows hold zeros in delta1 / delta2
-  int n_slices;                    // row slices per layer; grid = L * n_slices
-  int H;
 };
 
 // Arguments of the tcgen05 weight-gradient sweep (rnvp_wgrad_tc.cu): records as above but with the 3-bit slot swizzle,

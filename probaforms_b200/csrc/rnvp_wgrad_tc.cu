@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
   uint64_t* b_afull = b_hfree + NBUF;         // [NBUF]  delta1^T / h^T staged in TMEM (256 owner threads)
   uint64_t* b_accfull = b_afull + NBUF;       // [1]     an accumulator chain is complete (one commit per issuer)
   uint64_t* b_accfree = b_accfull + 1;        // [1]     ... and drained into registers (256 owner threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_accfree + 1);
+  uint64_t* b_img = b_accfree + 1;            // [1]     W2^T image staged in TMEM (256 owner threads), once per kernel
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_img + 1);
 
   const long long blocks_total = a.Npad / WT_ROWS;
   const long long blk0 = blocks_total * slice / a.n_slices, blk1 = blocks_total * (slice + 1) / a.n_slices;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 10); }
     for (int b = 0; b < NOP; ++b) { mbar_init(&b_conv[b], 64); mbar_init(&b_opfree[b], one_issuer ? 1 : 2); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(&b_dh[b], 1); mbar_init(&b_hfree[b], 1); mbar_init(&b_afull[b], 256); }
-    mbar_init(b_accfull, one_issuer ? 1 : 2); mbar_init(b_accfree, 256);
+    mbar_init(b_accfull, one_issuer ? 1 : 2); mbar_init(b_accfree, 256); mbar_init(b_img, 256);
     mbar_fence_init();
   }
   // zero the operand buffers once: padding columns (K1P8..NU) and padding K-groups are never written again
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
 
   if (warp == 0) {
     // ------------------------------------------------------------------ issuer A: dh^T and dW1
-    asm volatile("bar.sync 1, 288;" ::: "memory");             // the owners have staged the W2^T image in TMEM
+    mbar_wait(b_img, 0);                                       // the owners have staged the W2^T image in TMEM
     fence_after_sync();
     const bool leader = elect_one();
     const uint32_t idesc_dh = idesc_tf32(128, WT_ROWS), idesc_u = idesc_tf32(128, NU), idesc_u2 = idesc_tf32(128, 2 * NU);
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
       tmem_wait_st();
       fence_before_sync();
     }
-    asm volatile("bar.sync 1, 288;" ::: "memory");               // owners (256) + issuer A (32): the image is in place
+    mbar_arrive(b_img);                                          // the image is in place (issuer A waits for all 256 owners)
     // half 0 keeps the running sums of dW1 (this unit's row), half 1 those of dW2 (this unit's column, own net)
     constexpr int NS = NU > TP ? NU : TP;
     float sum[NS];
@@ -536,19 +537,14 @@ cudaError_t launch_tc(const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
 size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, int K1P8, int NN) {
   const size_t raw = (size_t)WT_ROWS * (128 + K1P8 + NN * TP);
   const size_t opf = 2 * (size_t)(NU / 8) * WT_NG + 2 * NN * (size_t)(TP / 8) * WT_NG + 2 * (size_t)WT_ROWS * NN * TP;
-  return (NSLOT * raw + NOP * opf) * 4 + 8 * (2 * NSLOT + 2 * NOP + 3 * NBUF + 2) + 64;
+  return (NSLOT * raw + NOP * opf) * 4 + 8 * (2 * NSLOT + 2 * NOP + 3 * NBUF + 3) + 64;
 }
 
 // D = 32 flows: NU 32, TP 16.  D = 64 flows: NU 48, TP 32 (one staging buffer: TMEM columns)
 cudaError_t rnvp_launch_wgrad_tc(int NU, int TP, const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
-  if (NU == 32 && TP == 16 && a.K1P8 == 24) {
-    const char* v = getenv("RNVP_WG_VARIANT");     // development knob: ring-depth experiments
-    const int var = v ? atoi(v) : 0;
-    if (var == 1) return launch_tc<32, 24, 16, 2, 2, 7>(a, grid, st);
-    if (var == 2) return launch_tc<32, 24, 16, 2, 3, 6>(a, grid, st);
-    if (var == 3) return launch_tc<32, 24, 16, 2, 2, 4>(a, grid, st);
-    return launch_tc<32, 24, 16, 2, 4, 4>(a, grid, st);
-  }
+  // ring depths measured on c3 (tools/wg_time.py): raw ring 4 / operand buffers 4 = 0.59 ms, 7 / 2 = 0.61, 6 / 3 = 0.59, 4 / 2 = 0.61:
+  // the sweep is not bound by bytes in flight
+  if (NU == 32 && TP == 16 && a.K1P8 == 24) return launch_tc<32, 24, 16, 2, 4, 4>(a, grid, st);
   if (NU == 32 && TP == 16 && a.K1P8 == 16) return launch_tc<32, 16, 16, 2, 4, 4>(a, grid, st);
   if (NU == 48 && TP == 32 && a.K1P8 == 48) return launch_tc<48, 48, 32, 1, 2, 3>(a, grid, st);
   // wide flows (rnvp_wide.cu fit sweeps): D = 128 (c5: K1P8 = 96, TP = 64), single-net lane blocks

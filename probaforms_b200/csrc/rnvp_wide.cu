@@ -55,7 +55,7 @@ __device__ __forceinline__ float exp_wide(float x) {
 }
 
 // barrier indices: ring full / empty first, then the tile hand-offs
-enum { WB_WF = 0, WB_WE = WD_STAGES, WB_UF = 2 * WD_STAGES, WB_D1F0, WB_D1F1, WB_AF0, WB_AF1, WB_D2F, WB_COUNT };
+enum { WB_WF = 0, WB_WE = WD_STAGES, WB_UF = 2 * WD_STAGES, WB_D1F0, WB_D1F1, WB_AF0, WB_AF1, WB_D2F, WB_XF, WB_XE, WB_COUNT };
 
 template <int DH, int CDMAX, int CU, int ACT, int MODE>
 __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_constant__ RnvpMmaArgs a) {
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
     mbar_init(&bars[WB_D1F0], 1); mbar_init(&bars[WB_D1F1], 1);
     mbar_init(&bars[WB_AF0], 256); mbar_init(&bars[WB_AF1], 256);
     mbar_init(&bars[WB_D2F], 1);
+    mbar_init(&bars[WB_XF], 128); mbar_init(&bars[WB_XE], 128);       // row-pair exchange of the partial log-dets / norms
     mbar_fence_init();
   }
   fence_before_sync();
@@ -438,21 +439,26 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
 #pragma unroll
         for (int e = 0; e < HALF; ++e) { q = fmaf(xa[e], xa[e], q); q = fmaf(xb[e], xb[e], q); }
         // the second thread of the row hands its partial sums to the first
-        if (half == 1) { xch[2 * rin] = ld; xch[2 * rin + 1] = q; }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
         float lp = 0.0f;
-        if (half == 0 && valid) {
+        if (half == 1) {
+          if (it > 0) mbar_wait(&bars[WB_XE], (uint32_t)((it - 1) & 1));          // the first threads have read the previous tile's sums
+          xch[2 * rin] = ld; xch[2 * rin + 1] = q;
+          mbar_arrive(&bars[WB_XF]);
+        } else {
+          mbar_wait(&bars[WB_XF], (uint32_t)(it & 1));
           const float ldt = ld + xch[2 * rin], qt = q + xch[2 * rin + 1];
-          lp = ldt - 0.5f * (D * 1.8378770664093453f + qt);
-          if (a.out_logdet) a.out_logdet[row] = ldt;
-          if (a.out_logp) a.out_logp[row] = lp;
+          mbar_arrive(&bars[WB_XE]);
+          if (valid) {
+            lp = ldt - 0.5f * (D * 1.8378770664093453f + qt);
+            if (a.out_logdet) a.out_logdet[row] = ldt;
+            if (a.out_logp) a.out_logp[row] = lp;
+          }
         }
         if (MODE == 2 && a.loss_sum && half == 0) {
 #pragma unroll
           for (int m = 16; m >= 1; m >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, m);
           if (lane == 0) atomicAdd(a.loss_sum, lp);
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");   // xch is reused by the next tile
       }
 
       // ================================================================ backward sweep (fit step)
