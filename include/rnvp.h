@@ -162,6 +162,9 @@ void rnvp_perm_destroy(rnvp_perm* p);
  * host threads.  rnvp_host_copy is a multi-threaded memcpy (the .cpu().numpy() of realnvp.py:281 into a fresh array). */
 int rnvp_host_gather_rows(const void* src, int src_is_f64, int64_t width, const int64_t* idx, int64_t row0, int64_t n,
                           float* dst, int threads);
+/* X and C rows of one step in one pass over idx (src_c may be NULL) */
+int rnvp_host_gather_xc(const void* src_x, int x_is_f64, int64_t width_x, const void* src_c, int c_is_f64, int64_t width_c,
+                           const int64_t* idx, int64_t row0, int64_t n, float* dst_x, float* dst_c, int threads);
 int rnvp_host_copy(void* dst, const void* src, int64_t bytes, int threads);
 
 /* Development aid: when d_buf (device, 4*2048*2 int64) is non-null, CTA 0 of the tcgen05 fit kernel logs (tag, clock64)

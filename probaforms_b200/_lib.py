@@ -52,6 +52,8 @@ SIGNATURES = {
     "rnvp_perm_destroy": (None, [C.c_void_p]),
     "rnvp_host_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                         C.c_int]),
+    "rnvp_host_gather_xc": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                         C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]),
     "rnvp_host_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "rnvp_mma_selftest": (C.c_int, [c_f32_p, c_f32_p, c_f32_p, C.c_int, C.c_int, C.c_int, c_stream]),
     "rnvp_last_error": (C.c_char_p, []),

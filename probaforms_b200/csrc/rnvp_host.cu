@@ -10,6 +10,9 @@
 #include <stdint.h>
 #include <string.h>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include "../../include/rnvp.h"
@@ -31,16 +34,73 @@ void gather_range(const T* src, int64_t width, const int64_t* idx, int64_t row0,
   }
 }
 
+// Persistent worker pool (created on first use, one per process): spawning 8-16 std::threads per call costs ~0.3 ms, as
+// much as the gather of a 75,776-row batch itself.  run_threads splits [0, n) into contiguous ranges; the caller works too.
+class Pool {
+ public:
+  static Pool& get() { static Pool p; return p; }
+  template <typename F>
+  void run(int64_t n, int64_t min_per_thread, int threads, F f) {
+    int t = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads, kMax + 1), n / std::max<int64_t>(min_per_thread, 1)));
+    if (t <= 1) { f(0, n); return; }
+    std::unique_lock<std::mutex> call(call_mu_);                 // one parallel region at a time
+    ensure(t - 1);
+    const int64_t per = (n + t - 1) / t;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = [&](int w) { f(std::min(n, (int64_t)(w + 1) * per), std::min(n, (int64_t)(w + 2) * per)); };
+      active_ = t - 1; pending_ = t - 1; ++epoch_;
+    }
+    cv_.notify_all();
+    f(0, std::min(n, per));
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  static constexpr int kMax = 31;
+  Pool() = default;
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++epoch_; }
+    cv_.notify_all();
+    for (auto& th : workers_) th.join();
+  }
+  void ensure(int n) {
+    while ((int)workers_.size() < n) {
+      const int w = (int)workers_.size();
+      workers_.emplace_back([this, w] {
+        uint64_t seen = 0;
+        for (;;) {
+          std::function<void(int)> job;
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+            if (stop_) return;
+            seen = epoch_;
+            if (w >= active_) continue;
+            job = job_;
+          }
+          job(w);
+          {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+          }
+        }
+      });
+    }
+  }
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  std::function<void(int)> job_;
+  int active_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
 template <typename F>
-void run_threads(int64_t n, int64_t min_per_thread, int threads, F f) {
-  int t = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n / std::max<int64_t>(min_per_thread, 1)));
-  if (t <= 1) { f(0, n); return; }
-  std::vector<std::thread> pool;
-  const int64_t per = (n + t - 1) / t;
-  for (int i = 1; i < t; ++i) pool.emplace_back(f, std::min(n, i * per), std::min(n, (i + 1) * per));
-  f(0, std::min(n, per));
-  for (auto& th : pool) th.join();
-}
+void run_threads(int64_t n, int64_t min_per_thread, int threads, F f) { Pool::get().run(n, min_per_thread, threads, f); }
 
 }  // namespace
 
@@ -54,6 +114,21 @@ int rnvp_host_gather_rows(const void* src, int src_is_f64, int64_t width, const 
     else gather_range((const float*)src, width, idx, row0, r0, r1, dst);
   };
   run_threads(n, std::max<int64_t>(1, 65536 / width), threads, work);
+  return 0;
+}
+
+int rnvp_host_gather_xc(const void* src_x, int x_is_f64, int64_t width_x, const void* src_c, int c_is_f64, int64_t width_c,
+                           const int64_t* idx, int64_t row0, int64_t n, float* dst_x, float* dst_c, int threads) {
+  if (!src_x || !dst_x || width_x < 1 || n < 0 || row0 < 0 || (src_c && (!dst_c || width_c < 1))) return RNVP_EINVAL;
+  auto work = [=](int64_t r0, int64_t r1) {
+    if (x_is_f64) gather_range((const double*)src_x, width_x, idx, row0, r0, r1, dst_x);
+    else gather_range((const float*)src_x, width_x, idx, row0, r0, r1, dst_x);
+    if (src_c) {
+      if (c_is_f64) gather_range((const double*)src_c, width_c, idx, row0, r0, r1, dst_c);
+      else gather_range((const float*)src_c, width_c, idx, row0, r0, r1, dst_c);
+    }
+  };
+  run_threads(n, std::max<int64_t>(1, 32768 / (width_x + width_c)), threads, work);
   return 0;
 }
 

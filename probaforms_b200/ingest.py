@@ -189,9 +189,15 @@ class StepStreamer:
                     ev.synchronize()                # kernels of the step that last used this slot are done
                 idx = get_idx(hi)
                 sl = idx[lo:hi]
-                gather_into(self.lib, self.X, sl, 0, m, self.hx[s], threads)
-                if self.hc is not None:
-                    gather_into(self.lib, self.Cn, sl, 0, m, self.hc[s], threads)
+                rc = self.lib.rnvp_host_gather_xc(
+                    C.c_void_p(self.X.ctypes.data), 1 if self.X.dtype == np.float64 else 0, self.X.shape[1],
+                    C.c_void_p(self.Cn.ctypes.data) if self.Cn is not None else None,
+                    1 if (self.Cn is not None and self.Cn.dtype == np.float64) else 0,
+                    self.Cn.shape[1] if self.Cn is not None else 0, C.c_void_p(sl.ctypes.data), 0, m,
+                    C.c_void_p(self.hx[s].data_ptr()), C.c_void_p(self.hc[s].data_ptr()) if self.hc is not None else None,
+                    threads)
+                if rc != 0:
+                    raise RuntimeError(f"rnvp_host_gather_xc failed (code {rc})")
                 with torch.cuda.stream(self.copy_stream):
                     self.dx[s][:m].copy_(self.hx[s][:m], non_blocking=True)
                     if self.hc is not None:
