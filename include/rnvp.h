@@ -127,6 +127,17 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
                    double weight_decay, int64_t step, int zero_gpacked, float* d_loss_src,
                    float* d_loss_dst, float loss_scale, void* stream);
 
+/* One epoch of the reference's fit loop (realnvp.py:238-254) as ONE call: for every consecutive slice of `batch_size`
+ * entries of the epoch's row order d_perm[n] (the last partial batch is kept): rnvp_backward with scale = -1/nb, then
+ * rnvp_adam_step (step count step0 + 1, step0 + 2, ...), the step's loss written to d_losses[s].  Same kernels and
+ * arithmetic as the two calls it wraps; it only removes the host-side per-step overhead, which dominates README-sized
+ * batches (32 rows: 2 launches of ~10 us against ~50 us of Python / ctypes).  Single GPU (no all-reduce between the two).
+ * d_gpacked and *d_loss_slot must be zero on entry and are zero again on return. */
+int rnvp_fit_epoch(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_gpacked, float* d_exp_avg, float* d_exp_avg_sq,
+                   const float* d_X, const float* d_C, const int64_t* d_perm, int64_t n, int64_t batch_size, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int64_t step0, float* d_loss_slot,
+                   float* d_losses, void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* Weight-gradient sweep from stored activations (last part of a fit step on the tcgen05 path): for every layer
  * dW1 += delta1^T u, db1 += sum delta1, dW2 += delta2^T h, db2 += sum delta2 (sums over rows), accumulated into
  * d_gpacked, with delta1 = (delta2 W2) * act'(h) recomputed from d_packed.  One record of

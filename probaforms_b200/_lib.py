@@ -43,6 +43,9 @@ SIGNATURES = {
     "rnvp_adam_step": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p,
                                  C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.c_int64, C.c_int, c_f32_p, c_f32_p, C.c_float, c_stream]),
+    "rnvp_fit_epoch": (C.c_int, [c_desc_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_f32_p, c_i64_p, C.c_int64,
+                                 C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, c_f32_p,
+                                 c_f32_p, C.c_void_p, C.c_int64, c_stream]),
     "rnvp_wgrad_record_floats": (C.c_int, [c_desc_p]),
     "rnvp_wgrad_sweep": (C.c_int, [c_desc_p, c_f32_p, C.c_int64, c_f32_p, c_f32_p, c_stream]),
     "rnvp_set_path": (C.c_int, [c_desc_p, C.c_int]),

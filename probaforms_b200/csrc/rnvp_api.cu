@@ -288,7 +288,12 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.wt_floats = records ? d->m_wt_floats : 0;
   a.trace = g_mma_trace;
   a.seed = seed; a.row_offset = row_offset;
-  if (d->m_stream || (d->m_netseq && mode == 2 && records)) {     // wide kernels: streamed images; the fit sweeps of every D >= 64 flow
+  // wide kernels (one tile per CTA, two threads per row, chunk images streamed): every D >= 64 flow -- measured on c4 they are
+  // 22 % faster than the resident-image kernel (129 vs 106 M rows/s log-prob) although the images would fit; RNVP_RESIDENT=1
+  // (development knob) keeps the resident kernel.  Only the hybrid fit (tensor-core forward + FP32 backward sweep, H not a
+  // multiple of 128) still needs the resident kernel's row-major stash.
+  static const bool keep_resident = [] { const char* e = getenv("RNVP_RESIDENT"); return e && atoi(e) != 0; }();
+  if (d->m_stream || (d->m_netseq && !(mode == 2 && !records) && !(keep_resident && mode != 2))) {
     if (mode == 2 && !records) return fail(RNVP_ESHAPE, "streamed tcgen05 kernels run the fit step with their own backward sweep only");
     const long long tiles = (N + 127) / 128;
     if (tiles > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
@@ -616,6 +621,25 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
       zero_gpacked, d_loss_src, d_loss_dst, loss_scale);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "adam_kernel");
+}
+
+int rnvp_fit_epoch(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_gpacked, float* d_exp_avg, float* d_exp_avg_sq,
+                   const float* d_X, const float* d_C, const int64_t* d_perm, int64_t n, int64_t batch_size, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int64_t step0, float* d_loss_slot,
+                   float* d_losses, void* d_workspace, int64_t workspace_bytes, void* stream) {
+  if (check_desc(d)) return RNVP_EINVAL;
+  if (n < 0 || batch_size < 1 || step0 < 0 || !d_perm || !d_losses || !d_loss_slot) return fail(RNVP_EINVAL, "rnvp_fit_epoch: bad argument");
+  int64_t s = 0;
+  for (int64_t b0 = 0; b0 < n; b0 += batch_size, ++s) {
+    const int64_t nb = std::min(batch_size, n - b0);
+    int rc = rnvp_backward(d, d_packed, d_X, d_C, d_perm + b0, nb, -1.0f / (float)nb, d_gpacked, d_loss_slot, nullptr, d_workspace,
+                           workspace_bytes, stream);
+    if (rc) return rc;
+    rc = rnvp_adam_step(d, d_flat, d_packed, d_gpacked, nullptr, d_exp_avg, d_exp_avg_sq, nullptr, 1.0f, lr, beta1, beta2, eps,
+                        weight_decay, step0 + s + 1, 1, d_loss_slot, d_losses + s, -1.0f / (float)nb, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int rnvp_wgrad_record_floats(const rnvp_desc* d) {

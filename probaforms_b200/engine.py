@@ -252,6 +252,22 @@ class FlowEngine:
                 C.c_float(loss_scale), self._stream()), "rnvp_adam_step")
         self.launches += 1
 
+    def fit_epoch(self, X, Cn, perm, n, batch_size, lr, weight_decay, losses, betas=(0.9, 0.999), eps=1e-8):
+        """All optimisation steps of one epoch in ONE library call (single GPU): consecutive ``batch_size`` slices of the row
+        order ``perm`` (device int64), losses[s] per step.  Removes the per-step Python / ctypes overhead that dominates
+        README-sized batches; same kernels as ``fit_step``."""
+        self._ensure_adam_state()
+        ws = self.workspace(min(int(batch_size), int(n)))
+        steps = (int(n) + int(batch_size) - 1) // int(batch_size)
+        with self._guard():
+            _lib.check(self.lib.rnvp_fit_epoch(
+                self._desc, _ptr(self.flat), _ptr(self.packed), _ptr(self.gpacked), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                _ptr(X), _ptr(Cn), _ptr(perm), int(n), int(batch_size), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                float(weight_decay), self.adam_steps, _ptr(self.loss_slot), _ptr(losses), _ptr(ws), ws.numel() * 4,
+                self._stream()), "rnvp_fit_epoch")
+        self.adam_steps += steps
+        self.launches += steps * ((2 if self._bwd_two_kernels else 1) + 1)
+
     # --------------------------------------------------------- one fit step
     def fit_step(self, X, Cn, idx, n_rows, n_global, lr, weight_decay, loss_dst, group=None, world=1):
         """loss=-mean logp over the global batch; backward; (all-reduce); Adam.  2 launches (+1 NCCL).

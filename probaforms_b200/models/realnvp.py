@@ -388,7 +388,18 @@ class RealNVP(GenModel):
                 perm_dev.copy_(perms.next(), non_blocking=True)
                 stream, copied = None, n
             perm_ptr = perm_dev.data_ptr()
-            for s, (b0, nb) in enumerate(bounds):           # last partial batch is kept (drop_last=False)
+            if world == 1 and bs <= 4096 and len(bounds) > 1:
+                # small batches: the host side of a step (Python + ctypes, ~50 us) costs more than its two kernels (~15 us), so
+                # the whole epoch goes down in one library call (rnvp_fit_epoch: same kernels, same order, same arithmetic)
+                if copied < n:
+                    host = stream.wait(n)
+                    perm_dev[copied:n].copy_(host[copied:n], non_blocking=True)
+                    copied = n
+                eng.fit_epoch(Xd, Cd, perm_dev, n, bs, self.lr, self.weight_decay, losses)
+                bounds_iter = ()
+            else:
+                bounds_iter = bounds
+            for s, (b0, nb) in enumerate(bounds_iter):      # last partial batch is kept (drop_last=False)
                 if copied < b0 + nb:                        # upload whatever is final by now, at least this batch
                     upto = max(b0 + nb, min(n, stream.available()))
                     host = stream.wait(upto)

@@ -1,32 +1,40 @@
-"""Where does RealNVP.fit(X_host, C_host) spend its wall time?  (development aid)"""
-import sys, time, torch
+"""Where does RealNVP.fit(X_numpy, C_numpy) spend its wall time?  (development aid)  Host gather rate by thread count, the
+pieces of one streamed step, and the whole call with both shuffles."""
+import sys, time, ctypes as C
+import numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from probaforms_b200.models import RealNVP
-import probaforms_b200.batching as B
-D, Cd, L, H, bs, steps = 32, 8, 16, 128, 75776, 16
-n = bs * steps
-g = torch.Generator().manual_seed(7)
-Xh = torch.randn(n, D, generator=g).pin_memory(); Ch = torch.randn(n, Cd, generator=g).pin_memory()
-m = RealNVP(n_layers=L, hidden=(H,), batch_size=bs, n_epochs=1, lr=1e-4)
-torch.manual_seed(0)
-m.fit(Xh[:2 * bs], Ch[:2 * bs])
-torch.cuda.synchronize()
-T = {}
-def tick(k, t0): T[k] = T.get(k, 0.0) + (time.perf_counter() - t0) * 1e3
-# H2D alone
-t = time.perf_counter(); Xd = Xh.to('cuda', non_blocking=True); Cd_ = Ch.to('cuda', non_blocking=True); torch.cuda.synchronize(); tick('h2d_194MB', t)
-# shuffle alone
-import ctypes as C
-lib = m.nf._fused().lib
-t = time.perf_counter(); sp = B.StreamingPermutation(lib, 123, n); tick('perm_create', t)
-t = time.perf_counter(); sp.wait(bs); tick('perm_first_batch', t)
-t = time.perf_counter(); sp.full(); tick('perm_rest', t)
-# whole fit
-t = time.perf_counter(); m.fit(Xh, Ch); torch.cuda.synchronize(); tick('fit_total', t)
-# fit with wait instrumentation
-orig_wait = B.StreamingPermutation.wait
-def wait(self, upto):
-    t0 = time.perf_counter(); r = orig_wait(self, upto); tick('wait_in_fit', t0); return r
-B.StreamingPermutation.wait = wait
-t = time.perf_counter(); m.fit(Xh, Ch); torch.cuda.synchronize(); tick('fit_total_2', t)
-print({k: round(v, 2) for k, v in T.items()}, 'gpu-only estimate ms', steps * 1.585)
+from probaforms_b200 import _lib
+import probaforms_b200.ingest as I
+lib = _lib.load()
+D, Cd, L, H, bs = 32, 8, 16, 128, 75776
+n = bs * 66
+rng = np.random.default_rng(0)
+blk = rng.standard_normal((1 << 20, D + Cd))
+XC = np.tile(blk, ((n + len(blk) - 1) // len(blk), 1))[:n]
+X, Cn = np.ascontiguousarray(XC[:, :D]), np.ascontiguousarray(XC[:, D:])
+idx = rng.permutation(n).astype(np.int64)
+hx = torch.empty(bs, D, pin_memory=True); hc = torch.empty(bs, Cd, pin_memory=True)
+for thr in (1, 4, 8, 12, 15):
+    ts = []
+    for k in range(12):
+        t0 = time.perf_counter()
+        lib.rnvp_host_gather_xc(C.c_void_p(X.ctypes.data), 1, D, C.c_void_p(Cn.ctypes.data), 1, Cd, C.c_void_p(idx[k * bs:].ctypes.data), 0, bs,
+                                C.c_void_p(hx.data_ptr()), C.c_void_p(hc.data_ptr()), thr)
+        ts.append(time.perf_counter() - t0)
+    print(f"gather f64 {bs} rows, {thr:2d} threads: median {sorted(ts)[6] * 1e3:.3f} ms  min {min(ts) * 1e3:.3f} ms")
+dx = torch.empty(bs, D, device='cuda'); dc = torch.empty(bs, Cd, device='cuda')
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(10):
+    dx.copy_(hx, non_blocking=True); dc.copy_(hc, non_blocking=True)
+torch.cuda.synchronize(); print(f"H2D of one step's rows: {(time.perf_counter() - t0) * 100:.3f} ms")
+print("host_threads()", I.host_threads())
+for shuffle in ("reference", "device"):
+    for ingest in ("stream", "resident"):
+        m = RealNVP(n_layers=L, hidden=(H,), batch_size=bs, n_epochs=1, lr=1e-4, shuffle=shuffle, ingest=ingest)
+        torch.manual_seed(0)
+        m.fit(X[:4 * bs], Cn[:4 * bs])
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        m.fit(X, Cn)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        print(f"fit {n} rows shuffle={shuffle:9s} ingest={ingest:8s}: {dt * 1e3:7.1f} ms = {n / dt / 1e6:.1f} M rows/s  ({dt / 66 * 1e3:.3f} ms/step)")
