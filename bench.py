@@ -606,7 +606,7 @@ def main():
             "achieved": executed, "peak": tf32_peak if on_tc else fp32_peak, "unit": "TFLOP/s",
             "frac": executed / (tf32_peak if on_tc else fp32_peak),
             "traffic": tr_total,
-            "kernel": ("rnvp_mma_kernel<16,8,32,0,1,2> (tcgen05 TF32x3 forward + backward sweeps) + rnvp_wgrad_tc_kernel "
+            "kernel": ("rnvp_wide_kernel<16,8,32,1,2> (tcgen05 TF32x3 forward + backward sweeps, two CTAs per SM) + rnvp_wgrad_tc_kernel "
                        "(tcgen05 TF32x3 weight-gradient sweep), timed together" if on_tc else
                        "rnvp_mma_kernel<..,2> (tcgen05 forward sweep) + rnvp_tile_kernel<TR,3> (FP32 backward sweep)"
                        if eng._bwd_two_kernels else "rnvp_tile_kernel<TR,2> (fused forward+backward)"),
@@ -651,14 +651,14 @@ def main():
             tk = (traffic or {}).get("kernels", {})
             mma_ms = kms - wgrad_ms
             line["roofline"]["kernels"] = {
-                "rnvp_mma_kernel<16,8,32,0,1,2>": {
+                "rnvp_wide_kernel<16,8,32,1,2>": {
                     "ms": mma_ms, "algorithmic_flops_per_row": f_fit - f_wgrad,
                     "executed_tf32_tflops": 3 * per_gpu * (f_fit - f_wgrad) / (mma_ms * 1e-3) / 1e12,
                     "frac_of_tf32_peak": 3 * per_gpu * (f_fit - f_wgrad) / (mma_ms * 1e-3) / 1e12 / tf32_peak,
                     "frac_of_mufu_peak": per_gpu * 2 * n_tanh / (mma_ms * 1e-3) / mufu_peak,
                     "designed_bytes_per_launch": per_gpu * bytes_row + per_gpu * L * D * 8 + rec_bytes + rec_bytes * 2 * H // eng.lib.rnvp_wgrad_record_floats(eng._desc),
-                    "measured_dram_bytes": tk.get("rnvp_mma_kernel", {}).get("dram_bytes"),
-                    "dram_frac_of_measured_peak": (tk["rnvp_mma_kernel"]["dram_bytes"] / (mma_ms * 1e-3) / 1e9 / hbm_peak) if "rnvp_mma_kernel" in tk else None,
+                    "measured_dram_bytes": tk.get("fit_sweep_kernel", {}).get("dram_bytes"),
+                    "dram_frac_of_measured_peak": (tk["fit_sweep_kernel"]["dram_bytes"] / (mma_ms * 1e-3) / 1e9 / hbm_peak) if "fit_sweep_kernel" in tk else None,
                     "bound": "latency / hand-offs: no unit above 0.6 (DESIGN.md 4.1c)",
                     "note": "forward sweep + backward sweep (dgrad); writes the activation records, reads h back"},
                 "rnvp_wgrad_tc_kernel<32,24,16,2,4,4>": {

@@ -53,6 +53,7 @@ struct FlowGeom {
   bool mma_ok = false;
   int mDH = 0, mCDMAX = 0, mCU = 0, mK1P = 0, mNTP = 0;
   bool m_netseq = false;
+  bool m_wide16 = false;   // D = 32 flows on the wide kernels too (two CTAs per SM); set by rnvp_desc_create (RNVP_WIDE16=0 turns it off)
   bool m_stream = false;   // weight images streamed per chunk step (rnvp_wide.cu) instead of resident per layer
   int m_w1_floats = 0, m_w2_floats = 0, m_b2_floats = 0, m_layer_floats = 0;
   int m_wt_floats = 0;   // transposed images for the backward sweep (W2T then W1T, m_wt_floats each), 0 if not built
@@ -119,7 +120,7 @@ inline void build_layout(FlowGeom* d) {
   if (nh == 1 && D % 2 == 0 && (D / 2 == 16 || D / 2 == 32 || D / 2 == 64)) {
     const int DH = D / 2, H = d->hidden[0];
     const int CDMAX = DH == 16 ? 8 : (DH == 32 ? 16 : 32), CU = 32;
-    const bool netseq = DH >= 32;                              // nn_t chunks before nn_s chunks (rnvp_mma.cu / rnvp_wide.cu)
+    const bool netseq = DH >= 32 || d->m_wide16;               // nn_t chunks before nn_s chunks (rnvp_mma.cu / rnvp_wide.cu)
     const int K1P = (DH + Cd + 1 + 7) & ~7, NTP = (DH + 15) & ~15;
     const int tile_cols = netseq ? 2 * K1P + 2 * CU + 2 * NTP : 2 * K1P + 4 * CU + 4 * NTP;
     const int64_t w1 = (int64_t)4 * H * K1P, w2 = (int64_t)4 * NTP * H;
@@ -138,7 +139,7 @@ inline void build_layout(FlowGeom* d) {
       // (resident kernels).  Streamed kernels: per chunk step (net, chunk of CU units) a W2T block [hi | lo] of [CU x DH] and
       // a W1T block [hi | lo] of [NTP x CU]; the tcgen05 weight-gradient sweep needs whole 128-unit lane blocks per net
       // (D = 64 flows with resident images, e.g. c4, run their FIT step on the streamed kernels too: same chunk images)
-      d->m_wt_floats = (!netseq && H % 16 == 0 && H <= 128) ? 4 * H * 16 : ((netseq && H % 128 == 0) ? 4 * H * NTP : 0);
+      d->m_wt_floats = (!netseq && H % 16 == 0 && H <= 128) ? 4 * H * 16 : ((netseq && (DH < 64 || H % 128 == 0)) ? 4 * H * NTP : 0);
       d->m_layer_floats = d->m_w1_floats + d->m_w2_floats + 2 * d->m_wt_floats;
       d->mma_off = (d->packed + 31) & ~(int64_t)31;            // 128-byte aligned for the bulk copies
       d->mma_floats = (int64_t)d->L * d->m_layer_floats;

@@ -54,11 +54,18 @@ __device__ __forceinline__ float exp_wide(float x) {
   return fmaf(e, r * 0.6931471805599453f, e);
 }
 
+// W consecutive TMEM columns of this thread's lane (W = 8 or 16)
+template <int W>
+__device__ __forceinline__ void tmem_ld_w(uint32_t taddr, uint32_t (&r)[W]) {
+  if constexpr (W == 16) tmem_ld_x16(taddr, r);
+  else tmem_ld_x8(taddr, r);
+}
+
 // barrier indices: ring full / empty first, then the tile hand-offs
 enum { WB_WF = 0, WB_WE = WD_STAGES, WB_UF = 2 * WD_STAGES, WB_D1F0, WB_D1F1, WB_AF0, WB_AF1, WB_D2F, WB_XF, WB_XE, WB_COUNT };
 
 template <int DH, int CDMAX, int CU, int ACT, int MODE>
-__global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_constant__ RnvpMmaArgs a) {
+__global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel(const __grid_constant__ RnvpMmaArgs a) {
   constexpr int K1PMAX = (DH + CDMAX + 1 + 7) & ~7;
   constexpr int NTP = (DH + 15) & ~15;
   constexpr int HALF = DH / 2;                         // features of each parity class owned by one thread of a row pair
@@ -70,6 +77,9 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
   // backward sweep (MODE 2): delta2 hi / lo (2 DH columns each), the dh / delta1 chunk ring, the du accumulators [main | corr]
   constexpr int E2H = 0, E2L = 2 * DH, DHB = 4 * DH, DUM = DHB + 4 * CU, DUC = DUM + NTP;
   static_assert(DUC + NTP <= 512, "TMEM budget (backward)");
+  // D = 32 flows need 224 columns in either sweep: two CTAs share an SM (256 columns each, 80 registers per thread)
+  constexpr int TALLOC = (TCOLS <= 256 && DUC + NTP <= 256) ? 256 : 512;
+  constexpr int CW = HALF >= 16 ? 16 : 8;               // columns per coupling / gradient piece
 
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -86,7 +96,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
   float* xch = reinterpret_cast<float*>(bars + WB_COUNT);                 // [128][2]: partial (logdet, |z|^2) of the second half-thread
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xch + 256);
 
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, TALLOC);
   if (tid == 0) {
     for (int s = 0; s < WD_STAGES; ++s) { mbar_init(&bars[WB_WF + s], 1); mbar_init(&bars[WB_WE + s], 1); }
     mbar_init(&bars[WB_UF], 256);
@@ -381,13 +391,13 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
             mbar_wait(&bars[WB_D2F], ph_d2); ph_d2 ^= 1;
             fence_after_sync();
 #pragma unroll
-            for (int e0 = 0; e0 < HALF; e0 += 16) {
-              uint32_t tv[16], tc[16];
-              tmem_ld_x16(trow + D2C + half * HALF + e0, tv);
-              tmem_ld_x16(trow + C2C + half * HALF + e0, tc);
+            for (int e0 = 0; e0 < HALF; e0 += CW) {
+              uint32_t tv[CW], tc[CW];
+              tmem_ld_w<CW>(trow + D2C + half * HALF + e0, tv);
+              tmem_ld_w<CW>(trow + C2C + half * HALF + e0, tc);
               tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) tpark[e0 + j] = __uint_as_float(tv[j]) + __uint_as_float(tc[j]);
+              for (int j = 0; j < CW; ++j) tpark[e0 + j] = __uint_as_float(tv[j]) + __uint_as_float(tc[j]);
             }
             fence_before_sync();                 // ordered before this thread's next a_full arrival, which releases D2 / C2
           }
@@ -396,13 +406,13 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
         mbar_wait(&bars[WB_D2F], ph_d2); ph_d2 ^= 1;
         fence_after_sync();
 #pragma unroll
-        for (int e0 = 0; e0 < HALF; e0 += 16) {
-          uint32_t sv[16], sc[16];
-          tmem_ld_x16(trow + D2C + half * HALF + e0, sv);
-          tmem_ld_x16(trow + C2C + half * HALF + e0, sc);
+        for (int e0 = 0; e0 < HALF; e0 += CW) {
+          uint32_t sv[CW], sc[CW];
+          tmem_ld_w<CW>(trow + D2C + half * HALF + e0, sv);
+          tmem_ld_w<CW>(trow + C2C + half * HALF + e0, sc);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < CW; ++j) {
             const float s = __uint_as_float(sv[j]) + __uint_as_float(sc[j]);
             const float t = tpark[e0 + j];
             if (MODE == 2) { sv[j] = __float_as_uint(s); sc[j] = __float_as_uint(xT[e0 + j]); }      // stash s and x_T
@@ -411,7 +421,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
           }
           if (MODE == 2 && do_bwd) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 0; m < CW / 4; ++m) {
               *reinterpret_cast<float4*>(stash_ptr(i, (half * HALF + e0) / 4 + m)) =
                   make_float4(__uint_as_float(sc[4 * m]), __uint_as_float(sc[4 * m + 1]), __uint_as_float(sc[4 * m + 2]),
                               __uint_as_float(sc[4 * m + 3]));
@@ -545,13 +555,13 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
             mbar_wait(&bars[WB_D2F], ph_d2); ph_d2 ^= 1;
             fence_after_sync();
 #pragma unroll
-            for (int e0 = 0; e0 < HALF; e0 += 16) {
-              uint32_t um[16], uc[16];
-              tmem_ld_x16(trow + DUM + half * HALF + e0, um);
-              tmem_ld_x16(trow + DUC + half * HALF + e0, uc);
+            for (int e0 = 0; e0 < HALF; e0 += CW) {
+              uint32_t um[CW], uc[CW];
+              tmem_ld_w<CW>(trow + DUM + half * HALF + e0, um);
+              tmem_ld_w<CW>(trow + DUC + half * HALF + e0, uc);
               tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) gK[e0 + j] += __uint_as_float(um[j]) + __uint_as_float(uc[j]);
+              for (int j = 0; j < CW; ++j) gK[e0 + j] += __uint_as_float(um[j]) + __uint_as_float(uc[j]);
             }
             fence_before_sync();
           };
@@ -566,7 +576,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1) rnvp_wide_kernel(const __grid_c
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tbase, 512);
+  if (warp == 1) tmem_dealloc(tbase, TALLOC);
 }
 
 template <int DH, int CDMAX>
@@ -600,5 +610,6 @@ size_t rnvp_wide_smem_bytes(int DH, int CDMAX) {
 cudaError_t rnvp_launch_wide(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, cudaStream_t st) {
   if (DH == 64) return launch_wide_shape<64, 32>(act, mode, a, grid, rnvp_wide_smem_bytes(64, 32), st);
   if (DH == 32) return launch_wide_shape<32, 16>(act, mode, a, grid, rnvp_wide_smem_bytes(32, 16), st);
+  if (DH == 16) return launch_wide_shape<16, 8>(act, mode, a, grid, rnvp_wide_smem_bytes(16, 8), st);
   return cudaErrorInvalidValue;
 }
