@@ -573,7 +573,11 @@ def main():
                "ingest": "stream: each rank gathers + converts + uploads only its shard of every batch, one step ahead",
                "api": "RealNVP.fit(X_numpy, C_numpy), n_epochs=1" + (", data-parallel (same host arrays on every rank)" if world > 1 else ""),
                "shuffle": "reference (default): batches composed exactly as the reference's DataLoader does",
-               "value_with_device_shuffle": n_e2e / dt_dev, "sample": e2e_sample}
+               "value_with_device_shuffle": n_e2e / dt_dev,
+               "device_shuffle_note": ("shuffle='device': GPU randperm per epoch" + (
+                   "; under data parallelism every rank uploads (sequentially, conversion fused) and shuffles only its own "
+                   "contiguous shard of the rows" if world > 1 else "")),
+               "sample": e2e_sample}
         del Xh, Ch
 
     if rank == 0:

@@ -351,6 +351,9 @@ class RealNVP(GenModel):
         stream_rows = mode == "stream" or (mode == "auto" and on_host and self.n_epochs <= world
                                            and min(bs, n) // world >= 8192)
         stream_rows = stream_rows and on_host and n > 0
+        if device_shuffle and world > 1 and mode != "stream" and n >= world:
+            # shuffle='device' under data parallelism: every rank keeps and shuffles its OWN contiguous shard of the rows
+            return self._fit_local_shards(X, C, eng, rank, world)
         # identical row order on every rank (the sampler seed of rank 0 is broadcast); computed one epoch ahead on a
         # helper thread, the first one while the rows are uploaded
         perms = None if device_shuffle else PermutationPrefetcher(
@@ -413,6 +416,43 @@ class RealNVP(GenModel):
             self.loss_history.extend(host.unbind(0))
             if bar is not None:
                 bar.set_description(f"loss: {float(host[-1]):.4f}")
+        self.opt._publish_state(eng)
+
+    def _fit_local_shards(self, X, C, eng, rank, world):
+        """Data-parallel fit with ``shuffle='device'``: rank r uploads only rows [n*r/world, n*(r+1)/world) of the (identical)
+        host arrays -- one sequential, chunked, conversion-fused upload instead of a random host gather per step or world
+        copies of the whole set -- and draws its own device permutation of that shard every epoch.  A global batch is the
+        union of the ranks' local batches of batch_size/world rows; the gradient all-reduce and the loss are scaled by the
+        true global row count of the step.  Statistically the same training as one GPU with ``shuffle='device'`` (uniform
+        batches without replacement within an epoch); not the reference's batch composition, like every ``'device'`` run.
+        The global torch RNG is consumed exactly as by the reference's loop (two int64 draws per epoch)."""
+        dev, n = self._device, X.shape[0]
+        lo_r, hi_r = (n * rank) // world, (n * (rank + 1)) // world
+        n_r = hi_r - lo_r
+        sizes = [(n * (r + 1)) // world - (n * r) // world for r in range(world)]
+        bs_r = max(1, int(self.batch_size) // world)
+        steps = (max(sizes) + bs_r - 1) // bs_r
+        Xd = self._to_device(X[lo_r:hi_r], dev)
+        Cd = self._to_device(C[lo_r:hi_r], dev) if C is not None else None
+        Xd = eng._check_rows(Xd, eng.D, "X")
+        Cd = eng._check_cond(Cd, n_r)
+        eng.zero_grads()
+        for _ in range(self.n_epochs):
+            seed = epoch_seed(device=dev)                          # same draws on every rank; rank 0's value is broadcast
+            gen = torch.Generator(device=dev)
+            gen.manual_seed((seed + 0x9E3779B97F4A7C15 * (rank + 1)) & 0x7FFFFFFFFFFFFFFF)
+            perm = torch.randperm(n_r, device=dev, generator=gen)
+            perm_ptr = perm.data_ptr()
+            losses = torch.empty(steps, dtype=torch.float32, device=dev)
+            loss_ptr = losses.data_ptr()
+            for s in range(steps):
+                b0 = s * bs_r
+                m = max(0, min(bs_r, n_r - b0))
+                n_glob = sum(max(0, min(bs_r, sz - b0)) for sz in sizes)
+                eng.fit_step(Xd, Cd, perm_ptr + 8 * b0, m, n_glob, self.lr, self.weight_decay, loss_ptr + 4 * s, world=world)
+            host = losses.cpu()
+            self.loss_history.extend(host.unbind(0))
+        self.h2d_bytes_last_fit = 4 * n_r * (eng.D + eng.Cd)
         self.opt._publish_state(eng)
 
     def _fit_streamed(self, X, C, eng, perms, bounds, rank, world, device_shuffle):
