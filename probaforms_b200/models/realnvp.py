@@ -351,8 +351,9 @@ class RealNVP(GenModel):
         stream_rows = mode == "stream" or (mode == "auto" and on_host and self.n_epochs <= world
                                            and min(bs, n) // world >= 8192)
         stream_rows = stream_rows and on_host and n > 0
-        if device_shuffle and world > 1 and mode != "stream" and n >= world:
-            # shuffle='device' under data parallelism: every rank keeps and shuffles its OWN contiguous shard of the rows
+        if device_shuffle and on_host and mode == "auto" and n >= world and min(bs, n) // world >= 4096:
+            # shuffle='device' from host data: every rank keeps and shuffles its OWN contiguous shard of the rows, and the
+            # first epoch trains while the shard is still being uploaded
             return self._fit_local_shards(X, C, eng, rank, world)
         # identical row order on every rank (the sampler seed of rank 0 is broadcast); computed one epoch ahead on a
         # helper thread, the first one while the rows are uploaded
@@ -419,39 +420,52 @@ class RealNVP(GenModel):
         self.opt._publish_state(eng)
 
     def _fit_local_shards(self, X, C, eng, rank, world):
-        """Data-parallel fit with ``shuffle='device'``: rank r uploads only rows [n*r/world, n*(r+1)/world) of the (identical)
-        host arrays -- one sequential, chunked, conversion-fused upload instead of a random host gather per step or world
-        copies of the whole set -- and draws its own device permutation of that shard every epoch.  A global batch is the
-        union of the ranks' local batches of batch_size/world rows; the gradient all-reduce and the loss are scaled by the
-        true global row count of the step.  Statistically the same training as one GPU with ``shuffle='device'`` (uniform
-        batches without replacement within an epoch); not the reference's batch composition, like every ``'device'`` run.
-        The global torch RNG is consumed exactly as by the reference's loop (two int64 draws per epoch)."""
+        """Fit with ``shuffle='device'`` from host arrays: rank r uploads only rows [n*r/world, n*(r+1)/world) of the
+        (identical) host arrays -- sequentially, in chunks, conversion fused (ingest.ChunkUploader) -- and shuffles that
+        shard on the device.  A global batch is the union of the ranks' local batches of batch_size/world rows; the
+        gradient all-reduce and the loss are scaled by the true global row count of the step.
+
+        The FIRST epoch of the call starts training while the shard is still arriving: its row order is the
+        concatenation of independent device permutations of consecutive chunks (a block-wise shuffle, as streaming data
+        loaders do), each chunk's steps waiting only for that chunk's upload, so the PCIe transfer hides behind the
+        kernels.  Later epochs use a full device permutation of the resident shard.  Statistically the same training
+        as ``shuffle='device'`` on one GPU; not the reference's batch composition, like every ``'device'`` run.  The
+        global torch RNG is consumed exactly as by the reference's loop (two int64 draws per epoch)."""
+        from ..ingest import ChunkUploader
         dev, n = self._device, X.shape[0]
         lo_r, hi_r = (n * rank) // world, (n * (rank + 1)) // world
         n_r = hi_r - lo_r
         sizes = [(n * (r + 1)) // world - (n * r) // world for r in range(world)]
         bs_r = max(1, int(self.batch_size) // world)
         steps = (max(sizes) + bs_r - 1) // bs_r
-        Xd = self._to_device(X[lo_r:hi_r], dev)
-        Cd = self._to_device(C[lo_r:hi_r], dev) if C is not None else None
-        Xd = eng._check_rows(Xd, eng.D, "X")
-        Cd = eng._check_cond(Cd, n_r)
+        chunk_rows = bs_r * max(1, min(8, (4 << 20) // max(bs_r * (eng.D + eng.Cd), 1) + 1))   # whole local batches per chunk
+        up = ChunkUploader(eng.lib, X[lo_r:hi_r], None if C is None else C[lo_r:hi_r], dev, chunk_rows)
+        Xd, Cd = up.X, up.C
         eng.zero_grads()
-        for _ in range(self.n_epochs):
-            seed = epoch_seed(device=dev)                          # same draws on every rank; rank 0's value is broadcast
+        for ep in range(self.n_epochs):
+            seed = epoch_seed(device=dev if world > 1 else None)   # same draws on every rank; rank 0's value is broadcast
             gen = torch.Generator(device=dev)
             gen.manual_seed((seed + 0x9E3779B97F4A7C15 * (rank + 1)) & 0x7FFFFFFFFFFFFFFF)
-            perm = torch.randperm(n_r, device=dev, generator=gen)
+            if ep == 0:
+                perm = torch.empty(max(n_r, 1), dtype=torch.int64, device=dev)
+                for c0 in range(0, n_r, chunk_rows):
+                    m = min(chunk_rows, n_r - c0)
+                    perm[c0:c0 + m] = torch.randperm(m, device=dev, generator=gen) + c0
+            else:
+                perm = torch.randperm(n_r, device=dev, generator=gen)
             perm_ptr = perm.data_ptr()
             losses = torch.empty(steps, dtype=torch.float32, device=dev)
             loss_ptr = losses.data_ptr()
             for s in range(steps):
                 b0 = s * bs_r
                 m = max(0, min(bs_r, n_r - b0))
+                if ep == 0 and m > 0:
+                    up.wait_rows(b0 + m)                            # the current stream waits for the chunk(s) holding these rows
                 n_glob = sum(max(0, min(bs_r, sz - b0)) for sz in sizes)
                 eng.fit_step(Xd, Cd, perm_ptr + 8 * b0, m, n_glob, self.lr, self.weight_decay, loss_ptr + 4 * s, world=world)
             host = losses.cpu()
             self.loss_history.extend(host.unbind(0))
+        up.close()
         self.h2d_bytes_last_fit = 4 * n_r * (eng.D + eng.Cd)
         self.opt._publish_state(eng)
 
