@@ -287,7 +287,7 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
   a.rec_swz = 7;
   a.wt_floats = records ? d->m_wt_floats : 0;
   a.trace = g_mma_trace;
-  a.seed = seed; a.row_offset = row_offset;
+  a.seed = seed; a.row_offset = row_offset; a.Dreal = d->D;
   // wide kernels (one tile per CTA, two threads per row, chunk images streamed): every D >= 64 flow -- measured on c4 they are
   // 22 % faster than the resident-image kernel (129 vs 106 M rows/s log-prob) although the images would fit; RNVP_RESIDENT=1
   // (development knob) keeps the resident kernel.  Only the hybrid fit (tensor-core forward + FP32 backward sweep, H not a
@@ -391,6 +391,7 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
         wl[i].w2_off[net] = g1.w_off[net]; wl[i].b2_off[net] = g1.b_off[net];
       }
       wl[i].Ks1 = g0.Ks; wl[i].Ks2 = g1.Ks;
+      wl[i].nK = d->layers[i].nK; wl[i].nT = d->layers[i].nT;
     }
     e = cudaMalloc(&d->d_wg, sizeof(RnvpWgradLayer) * wl.size());
     if (e == cudaSuccess) e = cudaMemcpy(d->d_wg, wl.data(), sizeof(RnvpWgradLayer) * wl.size(), cudaMemcpyHostToDevice);
@@ -666,12 +667,12 @@ int rnvp_wgrad_sweep(const rnvp_desc* dc, const float* d_packed, int64_t Npad, c
     // tcgen05 sweep: one CTA per (layer, block of 128 hidden units of [nn_t | nn_s], row slice), one wave of CTAs
     RnvpWgradTcArgs a;
     a.gR = d_records; a.rec = wgrad_rec_floats(d); a.Npad = Npad; a.H = d->hidden[0];
-    a.K1P8 = K1P; a.K1 = d->mDH + d->Cd; a.TP = TP; a.nT = d->mDH;
+    a.K1P8 = K1P; a.K1 = d->mDH + d->Cd; a.TP = TP; a.Cd = d->Cd;
     a.n_mblocks = (2 * d->hidden[0] + 127) / 128;
     a.n_slices = (int)std::max<long long>(1, std::min<long long>(Npad / 32, d->num_sms / (d->L * a.n_mblocks)));
     a.gpacked = d_gpacked; a.packed = d_packed; a.act = d->act; a.layers = d->d_wg; a.trace = g_mma_trace;
     { const char* o = getenv("RNVP_WG_ONE_ISSUER"); a.one_issuer = (o && atoi(o)) ? 1 : 0; }
-    const int NU = (K1P + 15) & ~15;
+    const int NU = TP == 16 ? 32 : (TP == 32 ? 48 : 96);           // dW1 tile columns of the three kernel variants (>= K1P8)
     cudaError_t e = rnvp_launch_wgrad_tc(NU, TP, a, d->L * a.n_mblocks * a.n_slices, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "rnvp_wgrad_tc_kernel");
   }

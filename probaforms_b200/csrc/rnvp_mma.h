@@ -32,4 +32,5 @@ struct RnvpMmaArgs {
   // MODE 1 with X == nullptr: latent rows drawn in-kernel (rnvp_philox.cuh), keyed on row_offset + row
   unsigned long long seed;
   long long row_offset;
+  int Dreal;                   // features per row in memory (rnvp_wide.cu: < 2 * DH for padded shapes, the row loads are guarded)
 };

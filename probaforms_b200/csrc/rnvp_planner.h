@@ -54,6 +54,7 @@ struct FlowGeom {
   int mDH = 0, mCDMAX = 0, mCU = 0, mK1P = 0, mNTP = 0;
   bool m_netseq = false;
   bool m_wide16 = false;   // D = 32 flows on the wide kernels too (two CTAs per SM); set by rnvp_desc_create (RNVP_WIDE16=0 turns it off)
+  bool m_padded = false;   // D != 2 * mDH: padded feature slots (wide kernels only)
   bool m_stream = false;   // weight images streamed per chunk step (rnvp_wide.cu) instead of resident per layer
   int m_w1_floats = 0, m_w2_floats = 0, m_b2_floats = 0, m_layer_floats = 0;
   int m_wt_floats = 0;   // transposed images for the backward sweep (W2T then W1T, m_wt_floats each), 0 if not built
@@ -117,10 +118,14 @@ inline void build_layout(FlowGeom* d) {
   // tcgen05 layout
   d->mma_ok = false;
   d->m_stream = false;
-  if (nh == 1 && D % 2 == 0 && (D / 2 == 16 || D / 2 == 32 || D / 2 == 64)) {
-    const int DH = D / 2, H = d->hidden[0];
-    const int CDMAX = DH == 16 ? 8 : (DH == 32 ? 16 : 32), CU = 32;
-    const bool netseq = DH >= 32 || d->m_wide16;               // nn_t chunks before nn_s chunks (rnvp_mma.cu / rnvp_wide.cu)
+  d->m_padded = false;
+  if (nh == 1 && D > 8 && D <= 128) {
+    // the kernels are built for DH = D/2 in {16, 32, 64}; any other D (odd ones included) runs as the next larger shape
+    // with zero-weight padding features: |K|, |T| <= DH, the images hold zeros beyond them, the row loads are guarded
+    const int DH = D <= 32 ? 16 : (D <= 64 ? 32 : 64), H = d->hidden[0];
+    d->m_padded = D != 2 * DH;
+    const int CDMAX = DH == 16 ? 16 : (DH == 32 ? 16 : 32), CU = 32;
+    const bool netseq = DH >= 32 || d->m_wide16 || d->m_padded || Cd > 8;   // (the resident D = 32 kernel: exact shape, Cd <= 8 only)               // nn_t chunks before nn_s chunks (rnvp_mma.cu / rnvp_wide.cu)
     const int K1P = (DH + Cd + 1 + 7) & ~7, NTP = (DH + 15) & ~15;
     const int tile_cols = netseq ? 2 * K1P + 2 * CU + 2 * NTP : 2 * K1P + 4 * CU + 4 * NTP;
     const int64_t w1 = (int64_t)4 * H * K1P, w2 = (int64_t)4 * NTP * H;
@@ -174,7 +179,7 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
           const int unit = (d->m_netseq ? cc % NC : cc) * CU + n % CU;
           for (int k = 0; k < K1P; ++k) {
             int64_t f = -1;
-            if (k < DH) f = g0.flat_w[net] + (int64_t)unit * (D + Cd) + (lg.par == 0 ? 2 * k + 1 : 2 * k);
+            if (k < DH) { const int xk = lg.par == 0 ? 2 * k + 1 : 2 * k; if (xk < D) f = g0.flat_w[net] + (int64_t)unit * (D + Cd) + xk; }
             else if (k < DH + Cd) f = g0.flat_w[net] + (int64_t)unit * (D + Cd) + D + (k - DH);
             else if (k == DH + Cd) f = g0.flat_b[net] + unit;
             if (f >= 0) m2f[blk + mma_tiled_off(n, k, K1P)] = (int)(4 * f + part);
@@ -189,6 +194,7 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
           const int64_t blk = base2 + (((int64_t)c * 2 + net) * 2 + part) * (NTP * CU);
           for (int r = 0; r < DH; ++r) {
             const int ft = lg.par == 0 ? 2 * r : 2 * r + 1;
+            if (ft >= D) continue;
             for (int kk = 0; kk < CU; ++kk)
               m2f[blk + mma_tiled_off(r, kk, CU)] = (int)(4 * (g1.flat_w[net] + (int64_t)ft * H + c * CU + kk) + part);
           }
@@ -200,6 +206,7 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
       for (int part = 0; part < 2; ++part)
         for (int r = 0; r < DH; ++r) {
           const int ft = lg.par == 0 ? 2 * r : 2 * r + 1;
+          if (ft >= D) continue;
           m2f[base3 + (net * 2 + part) * (NTP * 8) + mma_tiled_off(r, (DH + Cd) & 7, 8)] = (int)(4 * (g1.flat_b[net] + ft) + part);
         }
     if (d->m_wt_floats && d->m_netseq) {
@@ -216,8 +223,8 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
                 const int unit = c * CU + un;
                 const int ft = lg.par == 0 ? 2 * e : 2 * e + 1;            // transformed feature e
                 const int xk = lg.par == 0 ? 2 * e + 1 : 2 * e;            // conditioning feature e
-                m2f[o2 + mma_tiled_off(un, e, NTP)] = (int)(4 * (g1.flat_w[net] + (int64_t)ft * H + unit) + part);
-                m2f[o1 + mma_tiled_off(e, un, CU)] = (int)(4 * (g0.flat_w[net] + (int64_t)unit * (D + Cd) + xk) + part);
+                if (ft < D) m2f[o2 + mma_tiled_off(un, e, NTP)] = (int)(4 * (g1.flat_w[net] + (int64_t)ft * H + unit) + part);
+                if (xk < D) m2f[o1 + mma_tiled_off(e, un, CU)] = (int)(4 * (g0.flat_w[net] + (int64_t)unit * (D + Cd) + xk) + part);
               }
           }
     } else if (d->m_wt_floats) {

@@ -73,7 +73,7 @@ __device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(_
 
 // NU: columns of the dW1 tile (>= K1P8, multiple of 16); K1P8: u columns of a record; TP: delta2 columns per net (multiple of 16)
 // NBUF: TMEM staging buffers; NOP: operand buffers in shared memory; NSLOT: raw ring depth
-template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT, bool SINGLE>
+template <int NU, int TP, int NBUF, int NOP, int NSLOT, bool SINGLE>
 __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_kernel(const __grid_constant__ RnvpWgradTcArgs a) {
   // TMEM column map.  Per net the gradient accumulators sit side by side, [main | corr]: A_hi x [B_hi ; B_lo] is ONE MMA of
   // twice the width (the hi and lo operand tiles are adjacent in shared memory), A_lo x B_hi adds into the corr half.
@@ -86,11 +86,13 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
   constexpr int W2H = 0, W2L = NN * TP, STG0 = 2 * NN * TP, STGW = 128;         // staging: DH/D1H +0, D1L +32, HH +64, HL +96
   constexpr int ACC1 = STG0 + NBUF * STGW, ACC2 = ACC1 + (MERGED ? 2 * NU : NU), TCOLS = ACC2 + (MERGED ? 4 * TP : TP);
   static_assert(TCOLS <= 512, "TMEM budget");
-  static_assert(NU % 16 == 0 && TP % 16 == 0 && K1P8 % 8 == 0 && K1P8 <= NU, "N of an M=128 MMA is a multiple of 16");
+  static_assert(NU % 16 == 0 && TP % 16 == 0, "N of an M=128 MMA is a multiple of 16");
   constexpr int UB = (NU / 8) * WT_NG, EBN = (TP / 8) * WT_NG, DK = WT_ROWS * NN * TP;  // floats of one hi (or lo) tile
   constexpr int OPF = 2 * UB + 2 * NN * EBN + 2 * DK;                             // floats of one operand buffer
   // operand buffer: [u_hi | u_lo | e_t_hi | e_t_lo | e_s_hi | e_s_lo | dk_hi | dk_lo]
-  constexpr int RAW_H = WT_ROWS * 128, RAW_U = WT_ROWS * K1P8, RAW_E = WT_ROWS * NN * TP, RAW = RAW_H + RAW_U + RAW_E;
+  constexpr int RAW_H = WT_ROWS * 128, RAW_E = WT_ROWS * NN * TP;
+  const int K1P8 = a.K1P8;                                      // u columns of a record (multiple of 8, <= NU)
+  const int RAW_U = WT_ROWS * K1P8, RAW = RAW_H + RAW_U + RAW_E;
 
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -298,7 +300,8 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
   } else if (warp < 4) {
     // ------------------------------------------------------------------ converters (lanes = rows)
     const int cw = warp - 2;
-    constexpr int NCGU = K1P8 / 4, NCGE = (NN * TP) / 4, NUW = (NCGU + 1) / 2, NEW = NCGE / 2;
+    constexpr int NCGE = (NN * TP) / 4, NUW = (NU / 4 + 1) / 2, NEW = NCGE / 2;
+    const int NCGU = K1P8 / 4;
     const int cg_u0 = H2 >> 2, cg_e0 = (H2 + K1P8 + (SINGLE ? net_lo * TP : 0)) >> 2;                  // global column-group index (the slot swizzle uses it)
     float db2[NEW][4];
 #pragma unroll
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
 #pragma unroll
           for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
           const int e = 4 * cg + q, nl = e / TP, ee = e - nl * TP, net = SINGLE ? net_lo : nl;
-          if (lane == 0 && ee < a.nT) atomicAdd(a.gpacked + lw.b2_off[net] + ee, v);
+          if (lane == 0 && ee < lw.nT) atomicAdd(a.gpacked + lw.b2_off[net] + ee, v);
         }
       }
     }
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
         for (int j = 0; j < 8; ++j) {
           const int e = e0 + j, en = SINGLE ? net : e / TP, ee = SINGLE ? e : e - en * TP;
           float v = 0.0f;
-          if (valid && en == net && ee < a.nT) v = w2[ee * lw.Ks2 + unit];
+          if (valid && en == net && ee < lw.nT) v = w2[ee * lw.Ks2 + unit];
           hi[j] = __float_as_uint(v);
           lo[j] = __float_as_uint(lo_part(v));
         }
@@ -502,16 +505,24 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
     if (nst > 0 && valid) {
       if (half == 0) {
         float* gw1 = a.gpacked + lw.w1_off[net] + (size_t)unit * lw.Ks1;
+        if (lw.nK == a.TP) {   // exact shape: u = [x_K | c] has the packed row's column order
 #pragma unroll
-        for (int j = 0; j < NU; j += 4)
-          if (j < a.K1)        // K1 = |K| + Cd real columns; the packed row is padded to a multiple of 4
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gw1 + j), "f"(sum[j]), "f"(sum[j + 1]),
-                         "f"(sum[j + 2]), "f"(sum[j + 3]) : "memory");
+          for (int j = 0; j < NU; j += 4)
+            if (j < a.K1)      // K1 = |K| + Cd real columns; the packed row is padded to a multiple of 4
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gw1 + j), "f"(sum[j]), "f"(sum[j + 1]),
+                           "f"(sum[j + 2]), "f"(sum[j + 3]) : "memory");
+        } else {               // padded shape: the record's x_K part has TP slots, the packed row only |K|
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            if (j < lw.nK) atomicAdd(gw1 + j, sum[j]);
+            else if (j >= a.TP && j < a.TP + a.Cd) atomicAdd(gw1 + lw.nK + (j - a.TP), sum[j]);
+          }
+        }
       } else {
         float* gw2 = a.gpacked + lw.w2_off[net] + unit;
 #pragma unroll
         for (int e = 0; e < TP; ++e)
-          if (e < a.nT) atomicAdd(gw2 + (size_t)e * lw.Ks2, sum[e]);
+          if (e < lw.nT) atomicAdd(gw2 + (size_t)e * lw.Ks2, sum[e]);
       }
       atomicAdd(a.gpacked + lw.b1_off[net] + unit, db1);
     }
@@ -521,10 +532,10 @@ __global__ void __launch_bounds__(SINGLE ? 384 : WT_THREADS, 1) rnvp_wgrad_tc_ke
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
-template <int NU, int K1P8, int TP, int NBUF, int NOP, int NSLOT, bool SINGLE = false>
+template <int NU, int TP, int NBUF, int NOP, int NSLOT, bool SINGLE = false>
 cudaError_t launch_tc(const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
-  if (a.K1P8 != K1P8) return cudaErrorInvalidValue;
-  auto k = rnvp_wgrad_tc_kernel<NU, K1P8, TP, NBUF, NOP, NSLOT, SINGLE>;
+  if (a.K1P8 > NU || a.K1P8 % 8) return cudaErrorInvalidValue;
+  auto k = rnvp_wgrad_tc_kernel<NU, TP, NBUF, NOP, NSLOT, SINGLE>;
   const size_t smem = rnvp_wgrad_tc_smem_bytes(NU, TP, NBUF, NOP, NSLOT, a.K1P8, SINGLE ? 1 : 2);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -540,14 +551,13 @@ size_t rnvp_wgrad_tc_smem_bytes(int NU, int TP, int NBUF, int NOP, int NSLOT, in
   return (NSLOT * raw + NOP * opf) * 4 + 8 * (2 * NSLOT + 2 * NOP + 3 * NBUF + 3) + 64;
 }
 
-// D = 32 flows: NU 32, TP 16.  D = 64 flows: NU 48, TP 32 (one staging buffer: TMEM columns)
+// D <= 32 flows: NU 32, TP 16.  D <= 64: NU 48, TP 32 (one staging buffer: TMEM columns).  D <= 128: NU 96, TP 64, single-net
+// lane blocks (H a multiple of 128).  K1P8 = ceil8(DH + Cd) <= NU is a run-time value.
+// ring depths measured on c3 (tools/wg_time.py): raw ring 4 / operand buffers 4 = 0.59 ms, 7 / 2 = 0.61, 6 / 3 = 0.59, 4 / 2 = 0.61:
+// the sweep is not bound by bytes in flight
 cudaError_t rnvp_launch_wgrad_tc(int NU, int TP, const RnvpWgradTcArgs& a, int grid, cudaStream_t st) {
-  // ring depths measured on c3 (tools/wg_time.py): raw ring 4 / operand buffers 4 = 0.59 ms, 7 / 2 = 0.61, 6 / 3 = 0.59, 4 / 2 = 0.61:
-  // the sweep is not bound by bytes in flight
-  if (NU == 32 && TP == 16 && a.K1P8 == 24) return launch_tc<32, 24, 16, 2, 4, 4>(a, grid, st);
-  if (NU == 32 && TP == 16 && a.K1P8 == 16) return launch_tc<32, 16, 16, 2, 4, 4>(a, grid, st);
-  if (NU == 48 && TP == 32 && a.K1P8 == 48) return launch_tc<48, 48, 32, 1, 2, 3>(a, grid, st);
-  // wide flows (rnvp_wide.cu fit sweeps): D = 128 (c5: K1P8 = 96, TP = 64), single-net lane blocks
-  if (NU == 96 && TP == 64 && a.K1P8 == 96 && a.H % 128 == 0) return launch_tc<96, 96, 64, 1, 2, 2, true>(a, grid, st);
+  if (NU == 32 && TP == 16) return launch_tc<32, 16, 2, 4, 4>(a, grid, st);
+  if (NU == 48 && TP == 32) return launch_tc<48, 32, 1, 2, 3>(a, grid, st);
+  if (NU == 96 && TP == 64 && a.H % 128 == 0) return launch_tc<96, 64, 1, 2, 2, true>(a, grid, st);
   return cudaErrorInvalidValue;
 }

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
 
   extern __shared__ __align__(128) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = a.H, Cd = a.Cd, D = 2 * DH;
+  const int H = a.H, Cd = a.Cd, D = a.Dreal;           // D: features per row in memory; 2 * DH slots (padded shapes: D < 2 * DH)
+  const bool exact = D == 2 * DH;
   const int NC = H / CU, NCS = 2 * NC;                  // chunk steps per layer: nn_t chunks, then nn_s chunks
   const int K1P = (DH + Cd + 1 + 7) & ~7;
   const int nL = a.l1 - a.l0;
@@ -287,8 +288,20 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
 #pragma unroll
       for (int m = 0; m < HALF / 2; ++m) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 1 && a.X == nullptr) { if (valid) v = rnvp_rng::normal4(a.seed, a.row_offset + row, half * (DH / 4) + m); }
-        else if (valid) v = __ldg(reinterpret_cast<const float4*>(a.X + src * D + half * DH) + m);
+        const int j0 = half * DH + 4 * m;                 // first of this float4's feature slots
+        if (MODE == 1 && a.X == nullptr) { if (valid && j0 < D) v = rnvp_rng::normal4(a.seed, a.row_offset + row, half * (DH / 4) + m); }
+        else if (valid && exact) v = __ldg(reinterpret_cast<const float4*>(a.X + src * D + half * DH) + m);
+        else if (valid) {                                 // padded shape: row stride D, scalar guarded loads
+          const float* xr = a.X + src * D;
+          v.x = j0 + 0 < D ? __ldg(xr + j0 + 0) : 0.f; v.y = j0 + 1 < D ? __ldg(xr + j0 + 1) : 0.f;
+          v.z = j0 + 2 < D ? __ldg(xr + j0 + 2) : 0.f; v.w = j0 + 3 < D ? __ldg(xr + j0 + 3) : 0.f;
+        }
+        if (!exact) {                                     // slots beyond the row stay exactly zero (their weights are zero too)
+          if (j0 + 0 >= D) v.x = 0.f;
+          if (j0 + 1 >= D) v.y = 0.f;
+          if (j0 + 2 >= D) v.z = 0.f;
+          if (j0 + 3 >= D) v.w = 0.f;
+        }
         xa[2 * m] = v.x; xb[2 * m] = v.y; xa[2 * m + 1] = v.z; xb[2 * m + 1] = v.w;
       }
       // activation records of (layer i, this row): [layer][block of 32 rows][column group of 4][32 slots][4 floats], slot =
@@ -440,9 +453,21 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
       }
 
       if (valid && a.out_x) {
+        if (exact) {
 #pragma unroll
-        for (int m = 0; m < HALF / 2; ++m)
-          reinterpret_cast<float4*>(a.out_x + row * D + half * DH)[m] = make_float4(xa[2 * m], xb[2 * m], xa[2 * m + 1], xb[2 * m + 1]);
+          for (int m = 0; m < HALF / 2; ++m)
+            reinterpret_cast<float4*>(a.out_x + row * D + half * DH)[m] = make_float4(xa[2 * m], xb[2 * m], xa[2 * m + 1], xb[2 * m + 1]);
+        } else {
+          float* orow = a.out_x + row * D;
+#pragma unroll
+          for (int m = 0; m < HALF / 2; ++m) {
+            const int j0 = half * DH + 4 * m;
+            if (j0 + 0 < D) orow[j0 + 0] = xa[2 * m];
+            if (j0 + 1 < D) orow[j0 + 1] = xb[2 * m];
+            if (j0 + 2 < D) orow[j0 + 2] = xa[2 * m + 1];
+            if (j0 + 3 < D) orow[j0 + 3] = xb[2 * m + 1];
+          }
+        }
       }
       if (MODE != 1) {
         float q = 0.0f;
@@ -610,6 +635,6 @@ size_t rnvp_wide_smem_bytes(int DH, int CDMAX) {
 cudaError_t rnvp_launch_wide(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, cudaStream_t st) {
   if (DH == 64) return launch_wide_shape<64, 32>(act, mode, a, grid, rnvp_wide_smem_bytes(64, 32), st);
   if (DH == 32) return launch_wide_shape<32, 16>(act, mode, a, grid, rnvp_wide_smem_bytes(32, 16), st);
-  if (DH == 16) return launch_wide_shape<16, 8>(act, mode, a, grid, rnvp_wide_smem_bytes(16, 8), st);
+  if (DH == 16) return launch_wide_shape<16, 16>(act, mode, a, grid, rnvp_wide_smem_bytes(16, 16), st);
   return cudaErrorInvalidValue;
 }

@@ -86,6 +86,14 @@ def test_wide_d64_fit_gradients_tensor_core_path():
     _grad_check((64, 16, 3, (256,)), 3000, 3000, seed=15, gather=False, expect_tc_fit=None)
 
 
+@pytest.mark.parametrize("shape", [(24, 8, 3, (64,)), (9, 2, 4, (32,)), (48, 12, 2, (128,)), (100, 30, 2, (128,)), (16, 0, 3, (32,)),
+                                   (32, 16, 2, (64,))])
+def test_padded_shapes_fit_on_the_tensor_cores(shape):
+    """Flows whose D is not 32 / 64 / 128 (odd D included) run as the next larger kernel shape with zero-weight padding
+    features; the fit step stays on the tensor cores and its gradients meet the oracle (masked entries exact zeros)."""
+    _grad_check(shape, 3000 + shape[0], 4000, seed=30 + shape[0], gather=True, expect_tc_fit=True)
+
+
 def _fit_check(shape, n, bs, epochs, seed, **kw):
     from probaforms_b200.models import RealNVP
     D, Cd, L, hidden = shape

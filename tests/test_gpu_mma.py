@@ -33,7 +33,9 @@ def test_tcgen05_selftest(N, K):
 
 
 @pytest.mark.parametrize("shape", [(32, 8, 16, 128), (64, 16, 24, 128), (32, 0, 3, 64), (32, 5, 4, 256), (64, 16, 2, 32),
-                                   (128, 32, 8, 512), (128, 0, 2, 64), (128, 7, 3, 96), (64, 16, 3, 512)])
+                                   (128, 32, 8, 512), (128, 0, 2, 64), (128, 7, 3, 96), (64, 16, 3, 512),
+                                   # padded shapes: D != 2 * DH (odd D included), Cd up to 16 on the D <= 32 kernels
+                                   (16, 4, 3, 64), (24, 8, 3, 96), (48, 16, 2, 128), (9, 0, 3, 32), (100, 30, 2, 128), (32, 16, 2, 64)])
 @pytest.mark.parametrize("N", [1, 255, 257, 40000])
 def test_tcgen05_flow_matches_fp32_kernels(shape, N):
     """The tcgen05 (TF32x3) forward / inverse kernels against the FP32-FMA tile kernels of the same

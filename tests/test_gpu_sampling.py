@@ -10,7 +10,8 @@ from oracle import realnvp_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(2, 1, 8, (10,)), (32, 8, 4, (64,)), (64, 16, 3, (32,)), (7, 0, 5, (16, 12)), (5, 3, 4, (10,))]
+SHAPES = [(2, 1, 8, (10,)), (32, 8, 4, (64,)), (64, 16, 3, (32,)), (7, 0, 5, (16, 12)), (5, 3, 4, (10,)), (24, 8, 3, (64,)),
+          (9, 2, 3, (32,)), (128, 32, 2, (128,))]
 
 
 def _flow(shape, seed, dev):
