@@ -168,14 +168,16 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = 16384
+    rows = args.rows_per_gpu or per_gpu               # the same step as our arm: one optimisation step of the workload's batch
     rate, cores, step_s = cpu_port_step_rate(D, Cd, L, hidden, rows, reps=args.steps, warm=args.warmup)
     line = {
         "impl": "reference", "metric": "RealNVP fit rows/sec (fwd+bwd+Adam)", "value": rate, "unit": "rows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + " -- " + desc, "rows_per_step": rows,
-                   "note": "reference CPU path = oracle port (same ATen ops), bounded sample"},
+        "config": {"workload": args.workload + " -- " + desc, "D": D, "Cd": Cd, "n_layers": L, "hidden": list(hidden),
+                   "activation": "tanh", "rows_per_gpu_per_step": rows, "global_batch": rows,
+                   "note": "reference CPU path = oracle port (same ATen ops as realnvp.py:246-251), one host, all cores; each step is one "
+                           "optimisation step over the same batch size as the B200 arm"},
         "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} optimisation steps of {rows} rows"},
         "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
