@@ -44,9 +44,10 @@ constexpr int WT_KG = 36;                   // floats between K-groups (4 rows) 
 constexpr int WT_NG = 8 * WT_KG;            // floats between 8-column groups (SBO = 1152 B)
 constexpr int WT_FOLD = 4;                  // stages per accumulator chain (16 accumulations of K = 8)
 
-// Wait accounting (development aid, rnvp_debug_set_trace): when a trace buffer is set, every role of CTA 0 sums the cycles
+// Wait accounting (development aid, compile with -DRNVP_WG_TRACE; rnvp_debug_set_trace): when a trace buffer is set, every role of CTA 0 sums the cycles
 // it spends in each of its mbarrier waits and writes the totals at the end: trace[role * 8 + k] (role 0 issuer A, 1 issuer
 // B, 2 converter warp 2, 3 owner warp 4, 4 producer; k = wait site, 7 = total cycles of the role's loop).
+#ifdef RNVP_WG_TRACE
 struct WaitAcc {
   long long t[8];
   bool on;
@@ -68,6 +69,20 @@ struct WaitAcc {
     for (int k = 0; k < 8; ++k) out[role * 8 + k] = t[k];
   }
 };
+#else
+// production build: the accounting compiles away (even a disabled accumulator array costs registers in every role, and this
+// kernel is sensitive to that: a 720-byte per-thread event log made it 2x slower)
+struct WaitAcc {
+  static constexpr bool on = false;
+  long long t[8];
+  __device__ __forceinline__ void init(bool) {}
+  __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, int, bool relaxed = false) {
+    if (relaxed) tc05::mbar_wait_relaxed(bar, parity);
+    else tc05::mbar_wait(bar, parity);
+  }
+  __device__ __forceinline__ void flush(long long*, int, long long) {}
+};
+#endif
 
 __device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 

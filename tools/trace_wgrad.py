@@ -1,5 +1,7 @@
 """Wait accounting of CTA 0 of the tcgen05 weight-gradient sweep (rnvp_debug_set_trace): per role, the cycles spent in each
-mbarrier wait and the role's total loop time.  Shows which hand-off the kernel is bound by, without perturbing it."""
+mbarrier wait and the role's total loop time.  Needs a library built with -DRNVP_WG_TRACE (make -C probaforms_b200/csrc
+EXTRA=-DRNVP_WG_TRACE): the production build compiles the accounting away, because even the disabled accumulators cost the
+kernel 15 % (register pressure)."""
 import sys, ctypes as C, torch
 sys.path.insert(0, '/root/repo')
 from probaforms_b200.models import RealNVPLayer, NormalizingFlow
