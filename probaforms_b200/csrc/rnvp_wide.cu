@@ -13,7 +13,7 @@
 //   * the MMA issuer (warp 1, one elected lane) runs GEMM1 of chunk step cc+1 BEFORE it waits for the activations of chunk
 //     step cc, so the tensor core works on the next chunk while the epilogue warps turn the current one into tanh(.);
 //     error-compensated TF32 split as in rnvp_mma.cu (corrections first in GEMM1, merged A_hi x [B_hi ; B_lo] in GEMM2);
-//   * warps 4-11 are the epilogue: TWO THREADS PER ROW (a thread cannot hold a 128-D row): thread (row, half) owns half of
+//   * warps 2-9 are the epilogue: TWO THREADS PER ROW (a thread cannot hold a 128-D row): thread (row, half) owns half of
 //     the transformed and half of the conditioning features, writes its half of u, converts its 16 columns of every D1
 //     chunk and applies the coupling to its 32 features; the two partial log-dets / squared norms meet in shared memory.
 //   MODE 2 (fit step): the forward sweep additionally stashes (x_T, s) per layer and writes h = act(.) and u = [x_K, c] into
@@ -32,7 +32,7 @@
 namespace {
 using namespace tc05;
 
-constexpr int WD_THREADS = 384;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle, warps 4-11 epilogue
+constexpr int WD_THREADS = 320;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (TMEM lane quarter = warp % 4)
 constexpr int WD_STAGES = 4;          // weight ring depth (chunk steps in flight)
 
 template <int ACT>
@@ -272,9 +272,9 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ------------------------------------------------------------------ epilogue: two threads per row
-    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const uint32_t trow = tbase + ((uint32_t)(quarter * 32) << 16);
     const int rin = quarter * 32 + lane;                 // row inside the tile
     uint32_t ph_d1 = 0, ph_d2 = 0;
