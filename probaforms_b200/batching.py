@@ -40,14 +40,15 @@ class StreamingPermutation:
     """One epoch's row order, shuffled by a helper thread in ``chunk``-row steps through the C ABI
     (``rnvp_perm_*``, bit-identical to ``torch.randperm`` on the CPU): ``wait(upto)`` returns as soon as the first
     ``upto`` entries are final, so the fit loop consumes batch k while batch k+1.. are still being shuffled.
-    ``host`` is a (pinned, if CUDA is available) int64 buffer the caller copies slices from."""
+    ``host`` is an int64 buffer the caller copies slices from (pinned if ``pin`` and CUDA is available)."""
 
-    def __init__(self, lib, seed, n, host=None, chunk=16384):
+    def __init__(self, lib, seed, n, host=None, chunk=16384, pin=True):
         import ctypes as C
         import threading
         self.n, self.done = n, 0
         if host is None or host.numel() < n:
-            host = torch.empty(max(n, 1), dtype=torch.int64, pin_memory=torch.cuda.is_available())
+            # pinning costs ~2 ms per megabyte: only worth it when slices of the order are copied to the device
+            host = torch.empty(max(n, 1), dtype=torch.int64, pin_memory=bool(pin) and torch.cuda.is_available())
         self.host = host
         self._cv = threading.Condition()
         self._err = None
@@ -101,10 +102,10 @@ class PermutationPrefetcher:
     that will actually run, in order -- the global RNG is consumed exactly as by the reference's loop.
     """
 
-    def __init__(self, n, n_epochs, group=None, device=None, lib=None, host_buffers=None):
+    def __init__(self, n, n_epochs, group=None, device=None, lib=None, host_buffers=None, pin=True):
         import threading
         self._threading = threading
-        self.n, self.left, self.group, self.device = n, n_epochs, group, device
+        self.n, self.left, self.group, self.device, self.pin = n, n_epochs, group, device, pin
         self._thread, self._out = None, None
         # with the native library the order is streamed (StreamingPermutation); two host buffers alternate because the
         # next epoch is shuffled while the current one is still being consumed
@@ -121,7 +122,7 @@ class PermutationPrefetcher:
         self.left -= 1
         seed = epoch_seed(self.group, self.device)
         if self._lib is not None:
-            sp = StreamingPermutation(self._lib, seed, self.n, host=self._bufs[self._flip])
+            sp = StreamingPermutation(self._lib, seed, self.n, host=self._bufs[self._flip], pin=self.pin)
             self._bufs[self._flip] = sp.host
             self._flip ^= 1
             self._out, self._thread = {"stream": sp}, sp._thread

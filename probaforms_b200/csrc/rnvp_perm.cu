@@ -9,6 +9,8 @@
 #include <stdint.h>
 #include <new>
 #include <random>
+#include <thread>
+#include <vector>
 #include "../../include/rnvp.h"
 
 constexpr int PERM_AHEAD = 32;   // swap targets are drawn this many steps ahead and prefetched: the shuffle is bound by
@@ -43,7 +45,20 @@ int64_t rnvp_perm_advance(rnvp_perm* p, int64_t upto) {
   const int64_t n = p->n;
   int64_t* r = p->out;
   if (p->drawn < 0) {
-    for (int64_t k = 0; k < n; ++k) r[k] = k;
+    // identity fill (first touch of a fresh buffer: page faults): split over a few threads for large n so the first
+    // batch does not wait tens of milliseconds for it
+    const int nt = n >= (1 << 20) ? 8 : 1;
+    if (nt == 1) {
+      for (int64_t k = 0; k < n; ++k) r[k] = k;
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t)
+        th.emplace_back([=] {
+          const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+          for (int64_t k = lo; k < hi; ++k) r[k] = k;
+        });
+      for (auto& x : th) x.join();
+    }
     p->drawn = 0;
   }
   for (; i < upto && i < n - 1; ++i) {

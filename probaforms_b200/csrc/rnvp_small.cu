@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(THREADS) rnvp_small_kernel(const RnvpSmallArgs
 //
 // One thread owns one row through the whole flow: forward sweep (stashing x_T and s per layer in local memory), then
 // the backward sweep of d(scale * sum logp)/d(theta) with the hidden activations recomputed per unit (H is ~10).
-// Weight gradients are sums over rows: every per-row contribution is reduced over the warp with shuffles and added by
-// one lane to a shared-memory copy of the gradient (same layout as the weights, private to the CTA's single warp), which
+// Weight gradients are sums over rows: the per-row contributions are reduced over the warp with shuffles (32 values per
+// halving butterfly) and added by the owning lane to a shared-memory copy of the gradient (same layout as the weights, private to the CTA's single warp), which
 // is flushed once through the small-layout -> packed-gradient table.  A README-sized step (32 rows, 8 layers, H=10) is
 // one warp of one CTA instead of the ~190 us generic tile program for a single 32-row tile.
 constexpr int FIT_THREADS = 32;    // ONE warp per CTA: the shared-memory gradient copy is private to the warp, so its updates are plain
@@ -275,39 +275,60 @@ __device__ __forceinline__ void fit_bwd_layer(const float* __restrict__ wl, floa
     xT[e] = st_x[e];                                      // input of this layer
     du[e] = 0.0f;
   }
+  // Weight-gradient contributions of GJ hidden units at a time: the warp holds 32 per-row values V[jj * REC + q]; a
+  // halving butterfly (16 + 8 + 4 + 2 + 1 = 31 shuffles) leaves the row-sum of value l in lane l -- 5x fewer shuffles than
+  // one 5-step reduction per value, and the GJ units' recomputed activations overlap instead of running back to back.
+  constexpr int REC = 2 * NE + NC + 1;
+  constexpr int GJ = 32 / REC;
+  const int my_jj = lane / REC, my_q = lane - my_jj * REC;
 #pragma unroll
   for (int net = 0; net < 2; ++net) {
     const float* w = wl + net * net_floats;
     float* gw = gl + net * net_floats;
-    for (int j = 0; j < H; ++j) {
-      float rv[2 * NE + NC + 1];
-      load_record<NE, NC>(w + j * rec, rv);
-      float a = rv[NE + NC];
+    for (int j0 = 0; j0 < H; j0 += GJ) {
+      float V[32];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xK[e], a);
+      for (int i = GJ * REC; i < 32; ++i) V[i] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[k], a);
-      const float h = act_f<ACT>(a);
-      float dh = 0.0f;
+      for (int jj = 0; jj < GJ; ++jj) {
+        const int j = j0 + jj;
+        const bool live = j < H;
+        float rv[REC];
+        load_record<NE, NC>(w + (live ? j : 0) * rec, rv);
+        float a = rv[NE + NC];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) dh = fmaf(d2[net][e], rv[NE + NC + 1 + e], dh);
-      const float d1 = dh * (ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f));
+        for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xK[e], a);
 #pragma unroll
-      for (int e = 0; e < NE; ++e) du[e] = fmaf(d1, rv[e], du[e]);
-      // this row's contribution to the gradient of record j: [w1x | w1c | b1 | w2], reduced over the warp
-      float gv[2 * NE + NC + 1];
+        for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[k], a);
+        const float h = act_f<ACT>(a);
+        float dh = 0.0f;
 #pragma unroll
-      for (int e = 0; e < NE; ++e) gv[e] = d1 * xK[e];
+        for (int e = 0; e < NE; ++e) dh = fmaf(d2[net][e], rv[NE + NC + 1 + e], dh);
+        float d1 = dh * (ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f));
+        d1 = live ? d1 : 0.0f;
+        const float hl = live ? h : 0.0f;
 #pragma unroll
-      for (int k = 0; k < NC; ++k) gv[NE + k] = d1 * c[k];
-      gv[NE + NC] = d1;
+        for (int e = 0; e < NE; ++e) du[e] = fmaf(d1, rv[e], du[e]);
+        // this row's contribution to the gradient of record j: [w1x | w1c | b1 | w2]
 #pragma unroll
-      for (int e = 0; e < NE; ++e) gv[NE + NC + 1 + e] = d2[net][e] * h;
+        for (int e = 0; e < NE; ++e) V[jj * REC + e] = d1 * xK[e];
 #pragma unroll
-      for (int q = 0; q < 2 * NE + NC + 1; ++q) {
-        const float v = warp_sum(gv[q]);
-        if (lane == q) gw[j * rec + q] += v;              // entry q of every record is always updated by lane q
+        for (int k = 0; k < NC; ++k) V[jj * REC + NE + k] = d1 * c[k];
+        V[jj * REC + NE + NC] = d1;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) V[jj * REC + NE + NC + 1 + e] = d2[net][e] * hl;
       }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+          const float keep = up ? V[i + m] : V[i];
+          const float send = up ? V[i] : V[i + m];
+          V[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      if (my_jj < GJ && j0 + my_jj < H) gw[(j0 + my_jj) * rec + my_q] += V[0];     // lane l owns value l of the group
     }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {

@@ -20,6 +20,7 @@ import ctypes as C
 import os
 import queue
 import threading
+import time
 
 import numpy as np
 import torch
@@ -72,6 +73,73 @@ def _pinned(shape, key=None):
         buf = torch.empty(max(numel, 1), dtype=torch.float32, pin_memory=torch.cuda.is_available())
         _STAGING[key] = buf
     return buf[:numel].view(shape)
+
+
+class _LentBuffer:
+    """Owner of one pinned buffer that backs a numpy result: numpy keeps this object as the ``base`` of the array and of
+    every view derived from it, so the buffer goes back to the pool exactly when the last of them is garbage-collected."""
+
+    def __init__(self, pool, buf, shape):
+        self._pool, self._buf = pool, buf
+        self.__array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "<f4", "version": 3,
+                                    "data": (buf.data_ptr(), False)}
+
+    def __del__(self):
+        try:
+            self._pool._give_back(self._buf)
+        except Exception:                                   # interpreter shutdown
+            pass
+
+
+class ResultPool:
+    """Pinned host memory lent to the numpy arrays ``RealNVP.sample`` returns.
+
+    The reference returns ``.cpu().detach().numpy()`` (realnvp.py:281): a fresh pageable array, i.e. a D2H copy into a
+    bounce buffer plus a host copy whose first-touch page faults cost more than the bus transfer.  Here the D2H copy lands
+    directly in a pinned buffer that IS the returned array's memory; when the caller drops the array (and every view of
+    it) the buffer is recycled for the next call.  ``cap_bytes`` bounds the pinned memory out on loan + kept free; a
+    request that does not fit gets ``None`` and the caller falls back to a pageable array."""
+
+    def __init__(self, cap_bytes=4 << 30):
+        self.cap, self.total = int(cap_bytes), 0
+        self._free = []                                     # pinned flat float32 tensors
+        self._lock = threading.Lock()
+
+    def _give_back(self, buf):
+        with self._lock:
+            self._free.append(buf)
+
+    def lend(self, shape):
+        """(numpy float32 array of ``shape`` on pinned memory, flat torch view of the same memory) or (None, None)."""
+        numel = int(np.prod(shape))
+        if numel == 0 or not torch.cuda.is_available():
+            return None, None
+        with self._lock:
+            fit = [b for b in self._free if numel <= b.numel() <= 2 * numel]
+            buf = min(fit, key=lambda b: b.numel()) if fit else None
+            if buf is not None:
+                self._free = [b for b in self._free if b is not buf]
+            else:
+                need = 4 * numel
+                while self.total + need > self.cap and self._free:       # make room: drop idle buffers, largest first
+                    victim = max(self._free, key=lambda b: b.numel())
+                    self._free = [b for b in self._free if b is not victim]
+                    self.total -= 4 * victim.numel()
+                if self.total + need > self.cap:
+                    return None, None
+                self.total += need
+        if buf is None:
+            try:
+                buf = torch.empty(numel, dtype=torch.float32, pin_memory=True)
+            except RuntimeError:
+                with self._lock:
+                    self.total -= 4 * numel
+                return None, None
+        arr = np.asarray(_LentBuffer(self, buf, shape))
+        return arr, buf[:numel]
+
+
+RESULTS = ResultPool()
 
 
 def upload_resident(lib, A, dev, chunk_bytes=32 << 20):
@@ -244,12 +312,16 @@ class StepStreamer:
         self.hc = [_pinned((max_rows, wc), ("sc", k)) for k in range(self.SLOTS)] if wc else None
         self.dx = [torch.empty(max_rows, w, dtype=torch.float32, device=dev) for _ in range(self.SLOTS)]
         self.dc = [torch.empty(max_rows, wc, dtype=torch.float32, device=dev) for _ in range(self.SLOTS)] if wc else None
-        self.free = [None] * self.SLOTS            # event: the step that used the slot has finished
-        self.q = queue.Queue(maxsize=self.SLOTS - 1)
+        self.free = queue.Queue()                  # (slot, event): the step that used the slot was enqueued; event = it has run
+        for k in range(self.SLOTS):
+            self.free.put((k, None))
+        self.q = queue.Queue()
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.bytes_h2d = 0
         self._err = None
         self._plan = plan
+        self.trace = [] if os.environ.get("RNVP_INGEST_TRACE") else None    # (slot wait, order wait, gather, enqueue) seconds per step
+        self.trace_events = []                                              # (upload start, upload end) CUDA events per step
         self._thread = threading.Thread(target=self._work, daemon=True)
         self._thread.start()
 
@@ -258,13 +330,15 @@ class StepStreamer:
             torch.cuda.set_device(self.dev)
             threads = host_threads()
             for k, (get_idx, lo, hi) in enumerate(self._plan):
-                s = k % self.SLOTS
                 m = hi - lo
-                ev = self.free[s]
+                t0 = time.perf_counter()
+                s, ev = self.free.get()             # a slot the fit loop has released ...
                 if ev is not None:
-                    ev.synchronize()                # kernels of the step that last used this slot are done
+                    ev.synchronize()                # ... and whose step (upload + kernels) has run
+                t1 = time.perf_counter()
                 idx = get_idx(hi)
                 sl = idx[lo:hi]
+                t2 = time.perf_counter()
                 rc = self.lib.rnvp_host_gather_xc(
                     C.c_void_p(self.X.ctypes.data), 1 if self.X.dtype == np.float64 else 0, self.X.shape[1],
                     C.c_void_p(self.Cn.ctypes.data) if self.Cn is not None else None,
@@ -274,13 +348,21 @@ class StepStreamer:
                     threads)
                 if rc != 0:
                     raise RuntimeError(f"rnvp_host_gather_xc failed (code {rc})")
+                t3 = time.perf_counter()
                 with torch.cuda.stream(self.copy_stream):
+                    if self.trace is not None:
+                        up0 = torch.cuda.Event(enable_timing=True)
+                        up0.record(self.copy_stream)
                     self.dx[s][:m].copy_(self.hx[s][:m], non_blocking=True)
                     if self.hc is not None:
                         self.dc[s][:m].copy_(self.hc[s][:m], non_blocking=True)
-                    done = torch.cuda.Event()
+                    done = torch.cuda.Event(enable_timing=self.trace is not None)
                     done.record(self.copy_stream)
+                    if self.trace is not None:
+                        self.trace_events.append((up0, done))
                 self.bytes_h2d += 4 * m * (self.X.shape[1] + (self.Cn.shape[1] if self.Cn is not None else 0))
+                if self.trace is not None:
+                    self.trace.append((t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3, t0))
                 self.q.put((s, m, done))
             self.q.put(None)
         except BaseException as e:                  # surfaced by next()
@@ -302,7 +384,7 @@ class StepStreamer:
         """Call after the step's kernels were enqueued: the slot is recycled once they have run."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
-        self.free[slot] = ev
+        self.free.put((slot, ev))
 
     def close(self):
         self._thread.join()

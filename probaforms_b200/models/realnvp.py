@@ -252,6 +252,7 @@ class RealNVP(GenModel):
         self.loss_history = []
         self._device = None
         self._perm_host = [None, None]         # pinned staging buffers of the epoch row orders, reused across fits
+        self._perm_host_pageable = [None, None]  # the same for streamed ingestion (orders consumed on the host: not pinned)
 
     # ------------------------------------------------------------------ init
     def _model_init(self, X, C):
@@ -358,7 +359,9 @@ class RealNVP(GenModel):
         # identical row order on every rank (the sampler seed of rank 0 is broadcast); computed one epoch ahead on a
         # helper thread, the first one while the rows are uploaded
         perms = None if device_shuffle else PermutationPrefetcher(
-            n, self.n_epochs, device=dev if world > 1 else None, lib=eng.lib, host_buffers=self._perm_host)
+            n, self.n_epochs, device=dev if world > 1 else None, lib=eng.lib,
+            host_buffers=(self.__dict__.setdefault("_perm_host_pageable", [None, None]) if stream_rows else self._perm_host),
+            pin=not stream_rows)
         streamed_perm = perms is not None and perms.streaming
         bounds = batch_bounds(n, bs)
         if stream_rows:
@@ -571,18 +574,66 @@ class RealNVP(GenModel):
         if devices is not None and len(devices) > 0:
             out = self._sample_multi_device(C, is_int, lo, hi, seeds, list(devices))
         else:
-            Cd = None
-            if not is_int:
-                Cs = C[lo:hi]
-                Cd = self._to_device(Cs, self._device)
-            outs = [eng.sample(hi - lo, Cd, seed=sd, row_offset=lo) for sd in seeds]
-            out = torch.stack(outs) if n_draws is not None else outs[0]
-            return rows_to_numpy(eng.lib, out)
+            return self._sample_to_host(eng, None if is_int else C[lo:hi], lo, hi, seeds, n_draws is not None)
         return out if n_draws is not None else out[0]
+
+    def _sample_to_host(self, eng, Cs, lo, hi, seeds, stacked, chunk_rows=None):
+        """Rows [lo, hi) of every draw as ONE numpy array, pipelined in row chunks: the conditions of chunk k+1 go up and its
+        inverse kernel runs while chunk k's rows travel to the host.  The noise is keyed on the global row index, so the
+        chunking does not change a single value.  Large results land in pinned memory lent by ``ingest.RESULTS`` (it IS
+        the returned array's memory and is recycled when the caller drops the array); small ones, or a request beyond
+        the pool's cap, take the plain ``.cpu().numpy()`` / pageable path."""
+        from ..ingest import RESULTS, ChunkUploader, rows_to_numpy
+        dev, n, D = self._device, hi - lo, eng.D
+        shape = (len(seeds), n, D) if stacked else (n, D)
+        arr, flat = (None, None)
+        if n * D * 4 * len(seeds) > (1 << 20):
+            arr, flat = RESULTS.lend(shape)
+        if arr is None:
+            Cd = None if Cs is None else self._to_device(Cs, dev)
+            outs = [eng.sample(n, Cd, seed=sd, row_offset=lo) for sd in seeds]
+            return rows_to_numpy(eng.lib, torch.stack(outs) if stacked else outs[0])
+        host = flat.view(len(seeds), n, D)
+        chunk = int(chunk_rows or max(65536, min(n, (64 << 20) // (4 * D))))
+        chunk = max(1, min(chunk, n))
+        # the conditions go up chunk by chunk on a helper thread (conversion into pinned staging + H2D) while this thread
+        # already launches the kernels of the chunks that have arrived
+        on_dev = isinstance(Cs, torch.Tensor) and Cs.device.type != "cpu"
+        C_dev = self._to_device(Cs, dev) if on_dev else None
+        up = None if (Cs is None or on_dev) else ChunkUploader(eng.lib, Cs, None, dev, chunk)
+        slots = [torch.empty(chunk, D, dtype=torch.float32, device=dev) for _ in range(2)]
+        drained = [None, None]                               # D2H of the chunk that last used the slot
+        copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        k = 0
+        for r0 in range(0, n, chunk):
+            m = min(chunk, n - r0)
+            Cd = None if C_dev is None else C_dev[r0:r0 + m]
+            if up is not None:
+                up.wait_rows(r0 + m)
+                Cd = up.X[r0:r0 + m]
+            for j, sd in enumerate(seeds):
+                s = k & 1
+                if drained[s] is not None:
+                    cur.wait_event(drained[s])
+                y = eng.sample(m, Cd, seed=sd, row_offset=lo + r0, out=slots[s][:m])
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ready)
+                    host[j, r0:r0 + m].copy_(y, non_blocking=True)
+                    drained[s] = torch.cuda.Event()
+                    drained[s].record(copy_stream)
+                k += 1
+        if up is not None:
+            up.close()
+        copy_stream.synchronize()
+        return arr
 
     def _sample_multi_device(self, C, is_int, lo, hi, seeds, devices):
         """Row blocks of [lo, hi) on several GPUs of this process: replicas of the weights, one launch per (device, draw),
         results copied back into one host array."""
+        from ..ingest import _pinned
         n = hi - lo
         D = self.nf._fused(repack=False).D
         out = np.empty((len(seeds), n, D), dtype=np.float32)
@@ -596,7 +647,7 @@ class RealNVP(GenModel):
             with torch.cuda.device(dev):
                 Cd = None if is_int else self._to_device(C[b0:b1], dev)
                 res = torch.stack([eng.sample(b1 - b0, Cd, seed=sd, row_offset=b0) for sd in seeds])
-                host = torch.empty(res.shape, dtype=torch.float32, pin_memory=True)
+                host = _pinned(tuple(res.shape), ("mdev_x", k))
                 host.copy_(res, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
@@ -614,6 +665,7 @@ class RealNVP(GenModel):
             raise RuntimeError("RealNVP.log_prob_rows: call fit() first")
         n = X.shape[0]
         lo, hi = (self._shard_of(n)[:2] if shard else (0, n))
+        from ..ingest import _pinned
         devs = list(devices) if devices else [self._device]
         out = np.empty(hi - lo, dtype=np.float32)
         pending = []
@@ -627,7 +679,7 @@ class RealNVP(GenModel):
                 Xd = self._to_device(X[b0:b1], dev)
                 Cd = None if C is None else self._to_device(C[b0:b1], dev)
                 lp = eng.forward(Xd, Cd, want_z=False, want_logdet=False)[2]
-                host = torch.empty(lp.shape, dtype=torch.float32, pin_memory=True)
+                host = _pinned(tuple(lp.shape), ("mdev_lp", k))
                 host.copy_(lp, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
