@@ -9,6 +9,9 @@
 // rnvp_host_copy: multi-threaded memcpy (first-touch of a fresh numpy result array is page-fault bound on one thread).
 #include <stdint.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <condition_variable>
 #include <functional>
@@ -19,10 +22,22 @@
 
 namespace {
 
+#if defined(__SSE2__)
+// The staging buffers are read next by the GPU's DMA engine, not by this core: non-temporal stores keep 12 MB per step out
+// of the cores' caches (an upload whose source lines are dirty in 15 L2 caches was measured at 13 GB/s instead of 52).
+inline void store4(float* d, const float* s) { _mm_stream_ps(d, _mm_loadu_ps(s)); }
+inline void store4(float* d, const double* s) {
+  _mm_stream_ps(d, _mm_movelh_ps(_mm_cvtpd_ps(_mm_loadu_pd(s)), _mm_cvtpd_ps(_mm_loadu_pd(s + 2))));
+}
+#endif
+
 template <typename T>
 void gather_range(const T* src, int64_t width, const int64_t* idx, int64_t row0, int64_t r0, int64_t r1, float* dst) {
   constexpr int AHEAD = 16;                      // random rows: prefetch every cache line of the row 16 rows ahead
   const int64_t row_bytes = width * (int64_t)sizeof(T);
+#if defined(__SSE2__)
+  const bool stream_ok = width % 4 == 0 && ((uintptr_t)dst & 15) == 0;
+#endif
   for (int64_t r = r0; r < r1; ++r) {
     if (idx && r + AHEAD < r1) {
       const char* nx = (const char*)(src + idx[r + AHEAD] * width);
@@ -30,8 +45,17 @@ void gather_range(const T* src, int64_t width, const int64_t* idx, int64_t row0,
     }
     const T* s = src + (idx ? idx[r] : row0 + r) * width;
     float* d = dst + r * width;
+#if defined(__SSE2__)
+    if (stream_ok) {                               // 16-byte chunks with non-temporal stores (see store4)
+      for (int64_t j = 0; j < width; j += 4) store4(d + j, s + j);
+      continue;
+    }
+#endif
     for (int64_t j = 0; j < width; ++j) d[j] = (float)s[j];
   }
+#if defined(__SSE2__)
+  if (stream_ok) _mm_sfence();
+#endif
 }
 
 // Persistent worker pool (created on first use, one per process): spawning 8-16 std::threads per call costs ~0.3 ms, as

@@ -232,22 +232,35 @@ __device__ __forceinline__ void fit_fwd_layer(const float* __restrict__ wl, int 
   const int net_floats = H * rec + ((NE + 3) & ~3);
   float ts[2][NE];
 #pragma unroll
-  for (int net = 0; net < 2; ++net) {
-    const float* w = wl + net * net_floats;
+  for (int net = 0; net < 2; ++net)
 #pragma unroll
-    for (int e = 0; e < NE; ++e) ts[net][e] = w[H * rec + e];          // b2
-    for (int j = 0; j < H; ++j) {
-      float rv[2 * NE + NC + 1];
-      load_record<NE, NC>(w + j * rec, rv);
-      float a = rv[NE + NC];
+    for (int e = 0; e < NE; ++e) ts[net][e] = wl[net * net_floats + H * rec + e];          // b2
+  // the warp is alone on its scheduler: FU hidden units of BOTH nets are evaluated side by side so that their dependent
+  // chains (record load -> dot -> tanh -> W2 column) overlap instead of running one after the other
+  constexpr int FU = 5;
+  for (int j0 = 0; j0 < H; j0 += FU) {
+    float h[2][FU], rv[2][FU][2 * NE + NC + 1];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xK[e], a);
+    for (int jj = 0; jj < FU; ++jj)
 #pragma unroll
-      for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[k], a);
-      const float h = act_f<ACT>(a);
+      for (int net = 0; net < 2; ++net) load_record<NE, NC>(wl + net * net_floats + min(j0 + jj, H - 1) * rec, rv[net][jj]);
 #pragma unroll
-      for (int e = 0; e < NE; ++e) ts[net][e] = fmaf(rv[NE + NC + 1 + e], h, ts[net][e]);
-    }
+    for (int jj = 0; jj < FU; ++jj)
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+        float a = rv[net][jj][NE + NC];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) a = fmaf(rv[net][jj][e], xK[e], a);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a = fmaf(rv[net][jj][NE + k], c[k], a);
+        h[net][jj] = (j0 + jj < H) ? act_f<ACT>(a) : 0.0f;
+      }
+#pragma unroll
+    for (int jj = 0; jj < FU; ++jj)                        // same summation order over j as the one-unit-at-a-time loop
+#pragma unroll
+      for (int net = 0; net < 2; ++net)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) ts[net][e] = fmaf(rv[net][jj][NE + NC + 1 + e], h[net][jj], ts[net][e]);
   }
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
