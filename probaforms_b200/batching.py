@@ -72,8 +72,12 @@ class StreamingPermutation:
             finally:
                 lib.rnvp_perm_destroy(handle)
 
-        self._thread = threading.Thread(target=work, daemon=True)
-        self._thread.start()
+        if n <= 32768:                    # a fraction of a millisecond: cheaper than starting (and waking up for) a thread
+            work()
+            self._thread = None
+        else:
+            self._thread = threading.Thread(target=work, daemon=True)
+            self._thread.start()
 
     def wait(self, upto):
         upto = min(upto, self.n)
@@ -125,7 +129,7 @@ class PermutationPrefetcher:
             sp = StreamingPermutation(self._lib, seed, self.n, host=self._bufs[self._flip], pin=self.pin)
             self._bufs[self._flip] = sp.host
             self._flip ^= 1
-            self._out, self._thread = {"stream": sp}, sp._thread
+            self._out, self._thread = {"stream": sp}, (sp._thread or True)     # True: computed inline, nothing to join
             return
         out = {}
 

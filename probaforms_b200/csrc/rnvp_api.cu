@@ -172,13 +172,9 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packe
     if (zero_gpacked && p >= 0) gpacked[p] = 0.0f;
   }
   if (gflat_out) gflat_out[i] = g;
-  float th = theta[i];
-  if (wd != 0.0f) g = fmaf(wd, th, g);                 // grad.add(param, alpha=weight_decay)
   float mi = m[i], vi = v[i];
-  mi = fmaf(one_minus_b1, g - mi, mi);                 // exp_avg.lerp_(grad, 1-beta1)
-  vi = fmaf(one_minus_b2 * g, g, vi * b2);             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
-  const float denom = __fsqrt_rn(vi) / bc2_sqrt + eps; // (sqrt(v)/sqrt(bc2)).add_(eps)
-  th = fmaf(-step_size, mi / denom, th);               // param.addcdiv_(exp_avg, denom, value=-step_size)
+  const RnvpAdamCoef k{wd, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps};
+  const float th = rnvp_adam_update(g, theta[i], mi, vi, k);
   m[i] = mi; v[i] = vi; theta[i] = th;
   if (p >= 0) packed[p] = th;
   if (f2p2) {
@@ -231,12 +227,12 @@ int run_tile(rnvp_desc* d, int mode, int l0, int l1, RnvpKArgs& a, void* workspa
 }
 
 // fit step of small flows on the row-per-thread kernel (one launch, no workspace)
-bool use_small_fit(const rnvp_desc* d) { return d->small_ok && d->L <= rnvp_small_fit_max_layers() && d->small_floats * 8 <= d->max_smem; }
+bool use_small_fit(const rnvp_desc* d) { return d->small_ok && d->L <= rnvp_small_fit_max_layers() && d->small_floats * 12 + 4096 <= d->max_smem; }
 
 int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const float* X, const float* C,
               const long long* idx, long long N, float* out_x, float* out_logdet, float* out_logp, cudaStream_t stream,
               float* gpacked = nullptr, float* loss_sum = nullptr, float scale = 0.f, unsigned long long seed = 0,
-              long long row_offset = 0) {
+              long long row_offset = 0, const RnvpFusedAdam* fused = nullptr) {
   if (l0 < 0 || l1 > d->L || l0 >= l1) return fail(RNVP_EINVAL, "bad layer range");
   if (N <= 0) return 0;
   RnvpSmallArgs a;
@@ -247,6 +243,12 @@ int run_small(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const
   a.l0 = l0; a.l1 = l1;
   a.gpacked = gpacked; a.s2g = d->d_s2g; a.loss_sum = loss_sum; a.scale = scale;
   a.seed = seed; a.row_offset = row_offset;
+  a.fuse_adam = 0;
+  if (fused) {
+    if (mode != 2 || N > rnvp_small_fit_rows_per_block()) return fail(RNVP_EINVAL, "fused Adam needs a single-CTA fit step");
+    a.fuse_adam = 1;
+    a.ad = *fused;
+  }
   const long long rpb = mode == 2 ? rnvp_small_fit_rows_per_block() : rnvp_small_rows_per_block();
   const long long blocks = (N + rpb - 1) / rpb;
   const int grid = (int)std::min<long long>(blocks, (long long)d->num_sms * (mode == 2 ? 16 : 8));
@@ -635,8 +637,26 @@ int rnvp_fit_epoch(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
   if (check_desc(d)) return RNVP_EINVAL;
   if (n < 0 || batch_size < 1 || step0 < 0 || !d_perm || !d_losses || !d_loss_slot) return fail(RNVP_EINVAL, "rnvp_fit_epoch: bad argument");
   int64_t s = 0;
+  rnvp_desc* dm = const_cast<rnvp_desc*>(d);
   for (int64_t b0 = 0; b0 < n; b0 += batch_size, ++s) {
     const int64_t nb = std::min(batch_size, n - b0);
+    if (use_small_fit(dm) && nb <= rnvp_small_fit_rows_per_block() && (d->Cd > 0) == (d_C != nullptr) && d_X && d_flat && d_packed &&
+        d_exp_avg && d_exp_avg_sq) {
+      // the whole step is ONE single-CTA launch: fit kernel with the Adam update fused behind it (no packed-gradient round
+      // trip; d_gpacked and the loss slot stay zero, as the two-launch path leaves them)
+      const int64_t step = step0 + s + 1;
+      const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+      RnvpFusedAdam ad;
+      ad.theta = d_flat; ad.packed = d_packed; ad.m = d_exp_avg; ad.v = d_exp_avg_sq;
+      ad.f2p = d->d_f2p; ad.f2p2 = d->d_f2p2; ad.n = (int)d->P; ad.small_off = (int)d->small_off;
+      ad.k = RnvpAdamCoef{(float)weight_decay, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)(lr / bc1),
+                          (float)sqrt(bc2), (float)eps};
+      ad.loss_dst = d_losses + s; ad.loss_scale = -1.0f / (float)nb;
+      int rc = run_small(dm, 2, 0, d->L, d_packed, d_X, d_C, (const long long*)(d_perm + b0), nb, nullptr, nullptr, nullptr,
+                         (cudaStream_t)stream, d_gpacked, d_loss_slot, -1.0f / (float)nb, 0, 0, &ad);
+      if (rc) return rc;
+      continue;
+    }
     int rc = rnvp_backward(d, d_packed, d_X, d_C, d_perm + b0, nb, -1.0f / (float)nb, d_gpacked, d_loss_slot, nullptr, d_workspace,
                            workspace_bytes, stream);
     if (rc) return rc;

@@ -7,6 +7,9 @@
 // rnvp_perm_advance exposes exactly that: the fit loop starts on the first batches while a helper thread is still
 // shuffling the tail, instead of waiting tens of ns per row for the whole permutation up front.
 #include <stdint.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 #include <new>
 #include <random>
 #include <thread>
@@ -45,6 +48,16 @@ int64_t rnvp_perm_advance(rnvp_perm* p, int64_t upto) {
   const int64_t n = p->n;
   int64_t* r = p->out;
   if (p->drawn < 0) {
+#if defined(__linux__)
+    // every swap is one random access into an 8n-byte array: with 4 KB pages each one is also a TLB miss.  Ask for
+    // transparent huge pages on the whole-2MB part of the buffer before it is first touched (a hint: ignored where THP is
+    // off or the buffer is pinned / already faulted in).
+    if (n >= (1 << 18)) {
+      const uintptr_t a0 = ((uintptr_t)r + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+      const uintptr_t a1 = ((uintptr_t)(r + n)) & ~(uintptr_t)((2u << 20) - 1);
+      if (a1 > a0) madvise((void*)a0, a1 - a0, MADV_HUGEPAGE);
+    }
+#endif
     // identity fill (first touch of a fresh buffer: page faults): split over a few threads for large n so the first
     // batch does not wait tens of milliseconds for it
     const int nt = n >= (1 << 20) ? 8 : 1;

@@ -197,12 +197,17 @@ __global__ void __launch_bounds__(THREADS) rnvp_small_kernel(const RnvpSmallArgs
 //
 // One thread owns one row through the whole flow: forward sweep (stashing x_T and s per layer in local memory), then
 // the backward sweep of d(scale * sum logp)/d(theta) with the hidden activations recomputed per unit (H is ~10).
-// Weight gradients are sums over rows: the per-row contributions are reduced over the warp with shuffles (32 values per
-// halving butterfly) and added by the owning lane to a shared-memory copy of the gradient (same layout as the weights, private to the CTA's single warp), which
-// is flushed once through the small-layout -> packed-gradient table.  A README-sized step (32 rows, 8 layers, H=10) is
-// one warp of one CTA instead of the ~190 us generic tile program for a single 32-row tile.
-constexpr int FIT_THREADS = 32;    // ONE warp per CTA: the shared-memory gradient copy is private to the warp, so its updates are plain
-                                   // read-modify-writes by the owning lane (a float atomicAdd on shared memory is a CAS spin loop)
+// Fit step of a small flow.  32 rows per CTA, FOUR warps: warp w = (net = w & 1, half = w >> 1) evaluates half of the hidden
+// units of ONE conditioner for all 32 rows (lane = row); the partial t / s (forward) and du (backward) of the four warps
+// meet through a double-buffered shared-memory exchange and one __syncthreads per layer, after which every warp applies
+// the (cheap) coupling arithmetic redundantly, so all four hold the same row state.  A README-sized step (32 rows, 8 layers,
+// H = 10) is latency-bound on ONE warp's dependent instruction stream (IPC ~0.3); splitting the units over four warps cuts
+// that stream ~3x.  Weight gradients are sums over rows: the per-row contributions of up to 32 gradient entries are reduced
+// over the warp with one halving butterfly and added by the owning lane to a shared-memory copy of the gradient (each
+// warp touches only its own net's / units' entries), flushed once through the small-layout -> packed-gradient table.
+constexpr int FIT_WARPS = 4;
+constexpr int FIT_THREADS = 32 * FIT_WARPS;
+constexpr int FIT_ROWS = 32;       // rows per CTA
 constexpr int FIT_MAXL = 32;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -224,66 +229,70 @@ __device__ __forceinline__ void load_record(const float* __restrict__ u, float (
   }
 }
 
-// forward of one coupling layer for one row (same arithmetic, in the same order, as conditioner_pair + the MODE 0 update)
+// this warp's share of the work of a layer: conditioner `net`, hidden units [j_lo, j_hi)
+struct FitShare {
+  int net, j_lo, j_hi, wid, lane;
+  bool first_half;               // adds b2 (forward) / reduces the b2 gradient (backward)
+};
+
+// forward of one coupling layer (same arithmetic as conditioner_pair + the MODE 0 update; the sum over hidden units is split
+// into the two halves of the warps, then t = half0 + half1)
 template <int NE, int NC, int ACT>
-__device__ __forceinline__ void fit_fwd_layer(const float* __restrict__ wl, int H, int rec, float (&xT)[NE], const float (&xK)[NE],
-                                              const float (&c)[NC > 0 ? NC : 1], float* __restrict__ st_x,
-                                              float* __restrict__ st_s, float& ld) {
+__device__ __forceinline__ void fit_fwd_layer(const float* __restrict__ wl, int H, int rec, const FitShare& sh, float* __restrict__ xch,
+                                              float (&xT)[NE], const float (&xK)[NE], const float (&c)[NC > 0 ? NC : 1],
+                                              float* __restrict__ st_x, float* __restrict__ st_s, float& ld) {
   const int net_floats = H * rec + ((NE + 3) & ~3);
-  float ts[2][NE];
+  const float* w = wl + sh.net * net_floats;
+  float tp[NE];
 #pragma unroll
-  for (int net = 0; net < 2; ++net)
+  for (int e = 0; e < NE; ++e) tp[e] = sh.first_half ? w[H * rec + e] : 0.0f;          // b2
+  constexpr int FU = 5;          // units evaluated side by side: their dependent chains (record -> dot -> tanh -> W2) overlap
+  for (int j0 = sh.j_lo; j0 < sh.j_hi; j0 += FU) {
+    float h[FU], rv[FU][2 * NE + NC + 1];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) ts[net][e] = wl[net * net_floats + H * rec + e];          // b2
-  // the warp is alone on its scheduler: FU hidden units of BOTH nets are evaluated side by side so that their dependent
-  // chains (record load -> dot -> tanh -> W2 column) overlap instead of running one after the other
-  constexpr int FU = 5;
-  for (int j0 = 0; j0 < H; j0 += FU) {
-    float h[2][FU], rv[2][FU][2 * NE + NC + 1];
+    for (int jj = 0; jj < FU; ++jj) load_record<NE, NC>(w + min(j0 + jj, sh.j_hi - 1) * rec, rv[jj]);
+#pragma unroll
+    for (int jj = 0; jj < FU; ++jj) {
+      float a = rv[jj][NE + NC];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) a = fmaf(rv[jj][e], xK[e], a);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) a = fmaf(rv[jj][NE + k], c[k], a);
+      h[jj] = (j0 + jj < sh.j_hi) ? act_f<ACT>(a) : 0.0f;
+    }
 #pragma unroll
     for (int jj = 0; jj < FU; ++jj)
 #pragma unroll
-      for (int net = 0; net < 2; ++net) load_record<NE, NC>(wl + net * net_floats + min(j0 + jj, H - 1) * rec, rv[net][jj]);
-#pragma unroll
-    for (int jj = 0; jj < FU; ++jj)
-#pragma unroll
-      for (int net = 0; net < 2; ++net) {
-        float a = rv[net][jj][NE + NC];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) a = fmaf(rv[net][jj][e], xK[e], a);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) a = fmaf(rv[net][jj][NE + k], c[k], a);
-        h[net][jj] = (j0 + jj < H) ? act_f<ACT>(a) : 0.0f;
-      }
-#pragma unroll
-    for (int jj = 0; jj < FU; ++jj)                        // same summation order over j as the one-unit-at-a-time loop
-#pragma unroll
-      for (int net = 0; net < 2; ++net)
-#pragma unroll
-        for (int e = 0; e < NE; ++e) ts[net][e] = fmaf(rv[net][jj][NE + NC + 1 + e], h[net][jj], ts[net][e]);
+      for (int e = 0; e < NE; ++e) tp[e] = fmaf(rv[jj][NE + NC + 1 + e], h[jj], tp[e]);
   }
 #pragma unroll
+  for (int e = 0; e < NE; ++e) xch[(sh.wid * NE + e) * FIT_ROWS + sh.lane] = tp[e];
+  __syncthreads();
+#pragma unroll
   for (int e = 0; e < NE; ++e) {
+    const float t = xch[(0 * NE + e) * FIT_ROWS + sh.lane] + xch[(2 * NE + e) * FIT_ROWS + sh.lane];
+    const float sv = xch[(1 * NE + e) * FIT_ROWS + sh.lane] + xch[(3 * NE + e) * FIT_ROWS + sh.lane];
     st_x[e] = xT[e];
-    st_s[e] = ts[1][e];
-    xT[e] = fmaf(xT[e], expf(ts[1][e]), ts[0][e]);
-    ld += ts[1][e];
+    st_s[e] = sv;
+    xT[e] = fmaf(xT[e], expf(sv), t);
+    ld += sv;
   }
 }
 
-// backward of one coupling layer for one row; gl: this layer's slice of the shared-memory gradient accumulator
+// backward of one coupling layer; gl: this layer's slice of the shared-memory gradient accumulator
 template <int NE, int NC, int ACT>
-__device__ __forceinline__ void fit_bwd_layer(const float* __restrict__ wl, float* __restrict__ gl, int H, int rec, float (&xT)[NE],
-                                              const float (&xK)[NE], float (&gT)[NE], float (&gK)[NE],
-                                              const float (&c)[NC > 0 ? NC : 1], const float* __restrict__ st_x,
-                                              const float* __restrict__ st_s, float gld, int lane) {
+__device__ __forceinline__ void fit_bwd_layer(const float* __restrict__ wl, float* __restrict__ gl, int H, int rec, const FitShare& sh,
+                                              float* __restrict__ xch, float (&xT)[NE], const float (&xK)[NE], float (&gT)[NE],
+                                              float (&gK)[NE], const float (&c)[NC > 0 ? NC : 1], const float* __restrict__ st_x,
+                                              const float* __restrict__ st_s, float gld) {
   const int net_floats = H * rec + ((NE + 3) & ~3);
-  float d2[2][NE], du[NE];
+  const int lane = sh.lane;
+  float d2[NE], du[NE];
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
     const float es = expf(st_s[e]);
-    d2[0][e] = gT[e];                                     // dL/dt
-    d2[1][e] = fmaf(gT[e] * st_x[e], es, gld);            // dL/ds = g_y * x * exp(s) + g_logdet
+    d2[e] = sh.net == 0 ? gT[e]                           // dL/dt
+                        : fmaf(gT[e] * st_x[e], es, gld); // dL/ds = g_y * x * exp(s) + g_logdet
     gT[e] *= es;                                          // dL/dx_T
     xT[e] = st_x[e];                                      // input of this layer
     du[e] = 0.0f;
@@ -294,82 +303,98 @@ __device__ __forceinline__ void fit_bwd_layer(const float* __restrict__ wl, floa
   constexpr int REC = 2 * NE + NC + 1;
   constexpr int GJ = 32 / REC;
   const int my_jj = lane / REC, my_q = lane - my_jj * REC;
+  const float* w = wl + sh.net * net_floats;
+  float* gw = gl + sh.net * net_floats;
+  for (int j0 = sh.j_lo; j0 < sh.j_hi; j0 += GJ) {
+    float V[32];
 #pragma unroll
-  for (int net = 0; net < 2; ++net) {
-    const float* w = wl + net * net_floats;
-    float* gw = gl + net * net_floats;
-    for (int j0 = 0; j0 < H; j0 += GJ) {
-      float V[32];
+    for (int i = GJ * REC; i < 32; ++i) V[i] = 0.0f;
 #pragma unroll
-      for (int i = GJ * REC; i < 32; ++i) V[i] = 0.0f;
+    for (int jj = 0; jj < GJ; ++jj) {
+      const int j = j0 + jj;
+      const bool live = j < sh.j_hi;
+      float rv[REC];
+      load_record<NE, NC>(w + (live ? j : sh.j_lo) * rec, rv);
+      float a = rv[NE + NC];
 #pragma unroll
-      for (int jj = 0; jj < GJ; ++jj) {
-        const int j = j0 + jj;
-        const bool live = j < H;
-        float rv[REC];
-        load_record<NE, NC>(w + (live ? j : 0) * rec, rv);
-        float a = rv[NE + NC];
+      for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xK[e], a);
 #pragma unroll
-        for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xK[e], a);
+      for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[k], a);
+      const float h = act_f<ACT>(a);
+      float dh = 0.0f;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[k], a);
-        const float h = act_f<ACT>(a);
-        float dh = 0.0f;
+      for (int e = 0; e < NE; ++e) dh = fmaf(d2[e], rv[NE + NC + 1 + e], dh);
+      float d1 = dh * (ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f));
+      d1 = live ? d1 : 0.0f;
+      const float hl = live ? h : 0.0f;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) dh = fmaf(d2[net][e], rv[NE + NC + 1 + e], dh);
-        float d1 = dh * (ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f));
-        d1 = live ? d1 : 0.0f;
-        const float hl = live ? h : 0.0f;
+      for (int e = 0; e < NE; ++e) du[e] = fmaf(d1, rv[e], du[e]);
+      // this row's contribution to the gradient of record j: [w1x | w1c | b1 | w2]
 #pragma unroll
-        for (int e = 0; e < NE; ++e) du[e] = fmaf(d1, rv[e], du[e]);
-        // this row's contribution to the gradient of record j: [w1x | w1c | b1 | w2]
+      for (int e = 0; e < NE; ++e) V[jj * REC + e] = d1 * xK[e];
 #pragma unroll
-        for (int e = 0; e < NE; ++e) V[jj * REC + e] = d1 * xK[e];
+      for (int k = 0; k < NC; ++k) V[jj * REC + NE + k] = d1 * c[k];
+      V[jj * REC + NE + NC] = d1;
 #pragma unroll
-        for (int k = 0; k < NC; ++k) V[jj * REC + NE + k] = d1 * c[k];
-        V[jj * REC + NE + NC] = d1;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) V[jj * REC + NE + NC + 1 + e] = d2[net][e] * hl;
-      }
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < m; ++i) {
-          const float keep = up ? V[i + m] : V[i];
-          const float send = up ? V[i] : V[i + m];
-          V[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-        }
-      }
-      if (my_jj < GJ && j0 + my_jj < H) gw[(j0 + my_jj) * rec + my_q] += V[0];     // lane l owns value l of the group
+      for (int e = 0; e < NE; ++e) V[jj * REC + NE + NC + 1 + e] = d2[e] * hl;
     }
 #pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < m; ++i) {
+        const float keep = up ? V[i + m] : V[i];
+        const float send = up ? V[i] : V[i + m];
+        V[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+    if (my_jj < GJ && j0 + my_jj < sh.j_hi) gw[(j0 + my_jj) * rec + my_q] += V[0];     // lane l owns value l of the group
+  }
+  if (sh.first_half) {
+#pragma unroll
     for (int e = 0; e < NE; ++e) {
-      const float v = warp_sum(d2[net][e]);
+      const float v = warp_sum(d2[e]);
       if (lane == e) gw[H * rec + e] += v;                // b2
     }
   }
 #pragma unroll
-  for (int e = 0; e < NE; ++e) gK[e] += du[e];
+  for (int e = 0; e < NE; ++e) xch[(sh.wid * NE + e) * FIT_ROWS + lane] = du[e];
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < NE; ++e)
+    gK[e] += (xch[(0 * NE + e) * FIT_ROWS + lane] + xch[(1 * NE + e) * FIT_ROWS + lane]) +
+             (xch[(2 * NE + e) * FIT_ROWS + lane] + xch[(3 * NE + e) * FIT_ROWS + lane]);
 }
 
 template <int NE, int NC, int ACT>
 __global__ void __launch_bounds__(FIT_THREADS) rnvp_small_fit_kernel(const RnvpSmallArgs a) {
   extern __shared__ __align__(16) float wsm[];
   float* gsm = wsm + a.small_floats;
+  int* tsm = reinterpret_cast<int*>(gsm + a.small_floats);     // small layout -> packed-gradient index, staged with the weights:
+                                                               // the flush at the end must not pay a global-load latency per entry
+  float* xchg = reinterpret_cast<float*>(tsm + a.small_floats);                        // [2][FIT_WARPS][NE][FIT_ROWS]
   const int D = a.D, Cd = a.Cd, H = a.H, rec = a.rec, L = a.l1;
   for (int i = threadIdx.x * 4; i < a.small_floats; i += FIT_THREADS * 4) {
     *reinterpret_cast<float4*>(wsm + i) = *reinterpret_cast<const float4*>(a.packed_small + i);
     *reinterpret_cast<float4*>(gsm + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<int4*>(tsm + i) = *reinterpret_cast<const int4*>(a.s2g + i);
   }
   __syncthreads();
   const int layer_floats = 2 * (H * rec + ((NE + 3) & ~3));
-  const int lane = threadIdx.x & 31;
+  FitShare sh;
+  sh.lane = threadIdx.x & 31;
+  sh.wid = threadIdx.x >> 5;
+  sh.net = sh.wid & 1;
+  sh.first_half = (sh.wid >> 1) == 0;
+  const int per = (H + 1) / 2;
+  sh.j_lo = (sh.wid >> 1) * per;
+  sh.j_hi = min(H, sh.j_lo + per);
+  constexpr int XCH = FIT_WARPS * NE * FIT_ROWS;
   float loss_part = 0.0f;
 
-  // every lane of a warp runs the same number of iterations (the shuffles need the full warp); rows >= N carry zeros
-  for (long long base = (long long)blockIdx.x * FIT_THREADS; base < a.N; base += (long long)gridDim.x * FIT_THREADS) {
-    const long long row = base + threadIdx.x;
+  // every thread of the CTA runs the same number of iterations (shuffles and barriers need everyone); rows >= N carry zeros
+  for (long long base = (long long)blockIdx.x * FIT_ROWS; base < a.N; base += (long long)gridDim.x * FIT_ROWS) {
+    const long long row = base + sh.lane;
     const bool ok = row < a.N;
     const long long src = ok ? (a.idx ? a.idx[row] : row) : 0;
     float xe[NE], xo[NE], c[NC > 0 ? NC : 1], ld = 0.0f;
@@ -382,10 +407,13 @@ __global__ void __launch_bounds__(FIT_THREADS) rnvp_small_fit_kernel(const RnvpS
     for (int k = 0; k < (NC > 0 ? NC : 1); ++k) c[k] = (NC > 0 && ok && k < Cd) ? __ldg(a.C + src * Cd + k) : 0.0f;
 
     float st_x[FIT_MAXL][NE], st_s[FIT_MAXL][NE];        // per-layer stash (local memory, L1-resident)
-    for (int i = 0; i < L; ++i) {
+    int call = 0;                                         // exchange-buffer parity: consecutive layer calls alternate (2L calls per
+                                                          // row block, so the next block starts on the other buffer again)
+    for (int i = 0; i < L; ++i, ++call) {
       const float* wl = wsm + i * layer_floats;
-      if ((i & 1) == 0) fit_fwd_layer<NE, NC, ACT>(wl, H, rec, xe, xo, c, st_x[i], st_s[i], ld);
-      else fit_fwd_layer<NE, NC, ACT>(wl, H, rec, xo, xe, c, st_x[i], st_s[i], ld);
+      float* xch = xchg + (call & 1) * XCH;
+      if ((i & 1) == 0) fit_fwd_layer<NE, NC, ACT>(wl, H, rec, sh, xch, xe, xo, c, st_x[i], st_s[i], ld);
+      else fit_fwd_layer<NE, NC, ACT>(wl, H, rec, sh, xch, xo, xe, c, st_x[i], st_s[i], ld);
     }
     float q = 0.0f;
 #pragma unroll
@@ -394,7 +422,7 @@ __global__ void __launch_bounds__(FIT_THREADS) rnvp_small_fit_kernel(const RnvpS
       q = fmaf(xo[e], xo[e], q);
     }
     const float lp = ld - 0.5f * (D * 1.8378770664093453f + q);
-    if (ok) {
+    if (ok && sh.wid == 0) {
       if (a.out_logp) a.out_logp[row] = lp;
       loss_part += lp;
     }
@@ -403,20 +431,39 @@ __global__ void __launch_bounds__(FIT_THREADS) rnvp_small_fit_kernel(const RnvpS
     float ge[NE], go[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) { ge[e] = -gld * xe[e]; go[e] = -gld * xo[e]; }
-    for (int i = L - 1; i >= 0; --i) {
+    for (int i = L - 1; i >= 0; --i, ++call) {
       const float* wl = wsm + i * layer_floats;
       float* gl = gsm + i * layer_floats;
-      if ((i & 1) == 0) fit_bwd_layer<NE, NC, ACT>(wl, gl, H, rec, xe, xo, ge, go, c, st_x[i], st_s[i], gld, lane);
-      else fit_bwd_layer<NE, NC, ACT>(wl, gl, H, rec, xo, xe, go, ge, c, st_x[i], st_s[i], gld, lane);
+      float* xch = xchg + (call & 1) * XCH;
+      if ((i & 1) == 0) fit_bwd_layer<NE, NC, ACT>(wl, gl, H, rec, sh, xch, xe, xo, ge, go, c, st_x[i], st_s[i], gld);
+      else fit_bwd_layer<NE, NC, ACT>(wl, gl, H, rec, sh, xch, xo, xe, go, ge, c, st_x[i], st_s[i], gld);
     }
   }
-  if (a.loss_sum) {
+  if (a.fuse_adam) {
+    // single CTA: gsm holds the step's whole gradient (exactly what the flush below would have added to a zero accumulator)
+    if (sh.wid == 0 && a.ad.loss_dst) {
+      const float v = warp_sum(loss_part);
+      if (sh.lane == 0) *a.ad.loss_dst = v * a.ad.loss_scale;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.ad.n; i += FIT_THREADS) {
+      const int p = a.ad.f2p[i], p2 = a.ad.f2p2[i];
+      const float g = p2 >= 0 ? gsm[p2 - a.ad.small_off] : 0.0f;
+      float mi = a.ad.m[i], vi = a.ad.v[i];
+      const float th = rnvp_adam_update(g, a.ad.theta[i], mi, vi, a.ad.k);
+      a.ad.m[i] = mi; a.ad.v[i] = vi; a.ad.theta[i] = th;
+      if (p >= 0) a.ad.packed[p] = th;
+      if (p2 >= 0) a.ad.packed[p2] = th;
+    }
+    return;
+  }
+  if (a.loss_sum && sh.wid == 0) {
     const float v = warp_sum(loss_part);
-    if (lane == 0 && v != 0.0f) atomicAdd(a.loss_sum, v);
+    if (sh.lane == 0 && v != 0.0f) atomicAdd(a.loss_sum, v);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < a.small_floats; i += FIT_THREADS) {
-    const int t = a.s2g[i];
+    const int t = tsm[i];
     const float g = gsm[i];
     if (t >= 0 && g != 0.0f) atomicAdd(a.gpacked + t, g);
   }
@@ -426,8 +473,9 @@ template <int NE, int NC, int ACT>
 cudaError_t launch_mode(int mode, const RnvpSmallArgs& a, int grid, size_t smem, cudaStream_t st) {
   if (mode == 2) {
     auto k = rnvp_small_fit_kernel<NE, NC, ACT>;
-    if (2 * smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
-    k<<<grid, FIT_THREADS, 2 * smem, st>>>(a);
+    const size_t fit_smem = 3 * smem + 2 * FIT_WARPS * NE * FIT_ROWS * sizeof(float);
+    if (fit_smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem);
+    k<<<grid, FIT_THREADS, fit_smem, st>>>(a);
     return cudaGetLastError();
   }
   if (mode == 0) {
@@ -459,7 +507,7 @@ cudaError_t launch_nc(int NC, int act, int mode, const RnvpSmallArgs& a, int gri
 }  // namespace
 
 int rnvp_small_rows_per_block() { return THREADS * RPT; }
-int rnvp_small_fit_rows_per_block() { return FIT_THREADS; }
+int rnvp_small_fit_rows_per_block() { return FIT_ROWS; }
 int rnvp_small_fit_max_layers() { return FIT_MAXL; }
 
 cudaError_t rnvp_launch_small(int NE, int NC, int act, int mode, const RnvpSmallArgs& a, int grid, size_t smem,

@@ -1,6 +1,23 @@
 // Arguments of the row-per-thread small-flow kernels (rnvp_small.cu).
 #pragma once
 #include <stdint.h>
+#include "rnvp_adam.cuh"
+
+// Optional Adam update fused behind a fit step that runs as ONE CTA (rnvp_fit_epoch with batches of <= 32 rows, the
+// reference's default batch_size): the whole step's gradient is in the CTA's shared memory, so the optimiser update, the
+// refresh of the packed copies and the loss hand-off need neither the packed-gradient round trip nor a second launch.
+struct RnvpFusedAdam {
+  float* theta;                // flat parameters [n]
+  float* packed;               // packed copies (tile layout at f2p, small layout at f2p2)
+  float* m;
+  float* v;
+  const int* f2p;
+  const int* f2p2;             // absolute index of the small-layout copy in `packed`, or -1
+  int n, small_off;
+  RnvpAdamCoef k;
+  float* loss_dst;             // receives loss_scale * sum_rows logp (may be nullptr)
+  float loss_scale;
+};
 
 struct RnvpSmallArgs {
   const float* packed_small;   // per layer, per net: H records [w1_x NE | w1_c NC | b1 | w2 NE] (padded to rec), then b2
@@ -22,4 +39,6 @@ struct RnvpSmallArgs {
   // inverse mode with X == nullptr: the latent rows are drawn in-kernel (rnvp_philox.cuh), keyed on row_offset + row
   unsigned long long seed;
   long long row_offset;
+  int fuse_adam;               // fit step only, single-CTA launches only
+  RnvpFusedAdam ad;
 };

@@ -216,6 +216,42 @@ class FusedAdam(torch.optim.Adam):
         return loss
 
 
+class _LossLog:
+    """Per-step losses of ``fit`` -> ``loss_history`` (one 0-d CPU tensor per step, as upstream) without a device
+    synchronisation at the end of every epoch: an epoch's losses are copied to pinned memory asynchronously and collected
+    one epoch later, so the host prepares epoch e+1 (row order, uploads) while the GPU still runs epoch e."""
+
+    def __init__(self, history):
+        self.history, self.pending = history, None
+        self._stage, self._flip = [None, None], 0          # two pinned staging buffers alternate (allocating one per epoch
+                                                           # would cost more than the synchronisation it replaces)
+
+    def push(self, losses_dev):
+        """Call after the epoch's steps were enqueued; returns the PREVIOUS epoch's losses (CPU tensor) or None."""
+        k, n = self._flip, losses_dev.numel()
+        self._flip ^= 1
+        if self._stage[k] is None or self._stage[k].numel() < n:
+            self._stage[k] = torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True)
+        host = self._stage[k][:n]
+        host.copy_(losses_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(losses_dev.device))
+        prev, self.pending = self.pending, (host, ev, losses_dev)
+        return self._collect(prev)
+
+    def _collect(self, p):
+        if p is None:
+            return None
+        p[1].synchronize()
+        vals = p[0].clone()                     # off the pinned staging block
+        self.history.extend(vals.unbind(0))
+        return vals
+
+    def flush(self):
+        self._collect(self.pending)
+        self.pending = None
+
+
 class RealNVP(GenModel):
     """RealNVP normalizing flow (reference realnvp.py:133-282); parameters as upstream:
 
@@ -317,7 +353,7 @@ class RealNVP(GenModel):
 
         Per step: loss = -nf.log_prob(batch); zero_grad; backward; Adam step -- executed as one fused
         forward+backward launch plus one fused Adam launch.  ``loss_history`` gets one 0-d CPU tensor
-        per step (as upstream) but is synchronised once per epoch instead of every step.
+        per step (as upstream); an epoch's losses are read back one epoch later (no per-epoch device synchronisation).
 
         Under an initialised ``torch.distributed`` group every rank passes the SAME X, C; each
         global batch of ``batch_size`` rows is split into contiguous per-rank slices and the packed
@@ -379,7 +415,9 @@ class RealNVP(GenModel):
             bar = tqdm(epochs, unit='epoch')
             epochs = bar
         eng.zero_grads()
-        for _ in epochs:
+        log = _LossLog(self.loss_history)
+        order_copied = [None, None]                         # per host order buffer: its last H2D copy
+        for ep in epochs:
             # the epoch's row order streams in from a helper thread (rnvp_perm_*, same order as the reference's
             # DataLoader): a step only waits for its own batch, the tail of the shuffle overlaps the GPU work
             losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
@@ -390,6 +428,10 @@ class RealNVP(GenModel):
                 perm_dev = torch.randperm(n, device=dev, generator=gen)
                 stream, copied = None, n
             elif streamed_perm:
+                # next_stream() starts shuffling the epoch after this one into the host buffer the PREVIOUS epoch was copied
+                # from: its (asynchronous) copies must have run -- the loss read-back no longer synchronises every epoch
+                if order_copied[(ep + 1) & 1] is not None:
+                    order_copied[(ep + 1) & 1].synchronize()
                 stream, copied = perms.next_stream(), 0
             else:                                           # very large n: torch.randperm's 64-bit scheme, whole tensor
                 perm_dev.copy_(perms.next(), non_blocking=True)
@@ -416,10 +458,13 @@ class RealNVP(GenModel):
                 # raw device addresses instead of tensor slices: the host side of a 32-row step is the bottleneck
                 eng.fit_step(Xd, Cd, perm_ptr + 8 * lo, hi - lo, nb, self.lr, self.weight_decay,
                              loss_ptr + 4 * s, world=world)
-            host = losses.cpu()                             # the epoch's only device->host sync
-            self.loss_history.extend(host.unbind(0))
-            if bar is not None:
+            if streamed_perm and not device_shuffle:
+                order_copied[ep & 1] = torch.cuda.Event()            # epoch ep read host buffer ep & 1
+                order_copied[ep & 1].record(torch.cuda.current_stream(dev))
+            host = log.push(losses)                         # collects the previous epoch's losses: no sync on this one
+            if bar is not None and host is not None:
                 bar.set_description(f"loss: {float(host[-1]):.4f}")
+        log.flush()
         self.opt._publish_state(eng)
 
     def _fit_local_shards(self, X, C, eng, rank, world):
@@ -445,6 +490,7 @@ class RealNVP(GenModel):
         up = ChunkUploader(eng.lib, X[lo_r:hi_r], None if C is None else C[lo_r:hi_r], dev, chunk_rows)
         Xd, Cd = up.X, up.C
         eng.zero_grads()
+        log = _LossLog(self.loss_history)
         for ep in range(self.n_epochs):
             seed = epoch_seed(device=dev if world > 1 else None)   # same draws on every rank; rank 0's value is broadcast
             gen = torch.Generator(device=dev)
@@ -466,8 +512,8 @@ class RealNVP(GenModel):
                     up.wait_rows(b0 + m)                            # the current stream waits for the chunk(s) holding these rows
                 n_glob = sum(max(0, min(bs_r, sz - b0)) for sz in sizes)
                 eng.fit_step(Xd, Cd, perm_ptr + 8 * b0, m, n_glob, self.lr, self.weight_decay, loss_ptr + 4 * s, world=world)
-            host = losses.cpu()
-            self.loss_history.extend(host.unbind(0))
+            log.push(losses)
+        log.flush()
         up.close()
         self.h2d_bytes_last_fit = 4 * n_r * (eng.D + eng.Cd)
         self.opt._publish_state(eng)
@@ -477,8 +523,6 @@ class RealNVP(GenModel):
         batches are the same slices of the same epoch permutations as in resident mode, so the trajectory is identical."""
         from ..ingest import StepStreamer
         dev, n = self._device, X.shape[0]
-        epoch_orders = []                                   # one provider per epoch: get(hi) -> host int64 array
-
         def order_provider():
             if device_shuffle:
                 gen = torch.Generator(device=dev)
@@ -491,41 +535,29 @@ class RealNVP(GenModel):
             host = perms.next().numpy()
             return lambda hi: host
 
-        # seeds are drawn on this thread, in epoch order, exactly as in resident mode; epoch e+1's order is requested when
-        # epoch e starts so that at most two epoch orders are in flight (the prefetcher alternates two host buffers)
-        import threading
-        ready = [threading.Event() for _ in range(self.n_epochs)]
-        epoch_orders = [None] * self.n_epochs
-
+        # The streamer gathers on THIS thread, so the plan generator below runs here too: seeds are drawn in epoch order exactly
+        # as in resident mode, and epoch e+1's order is requested only after the last gather of epoch e -- the prefetcher then
+        # starts shuffling epoch e+2 into the host buffer epoch e has just finished with (two buffers alternate).
         def plan():
             for e in range(self.n_epochs):
-                ready[e].wait()
-                get = epoch_orders[e]
+                get = order_provider()
                 for (b0, nb) in bounds:
                     lo, hi = shard_bounds(b0, nb, rank, world)
                     yield get, lo, hi
 
         max_rows = max(shard_bounds(b0, nb, rank, world)[1] - shard_bounds(b0, nb, rank, world)[0] for b0, nb in bounds)
-        epoch_orders[0] = order_provider()
-        ready[0].set()
         streamer = StepStreamer(eng.lib, X, C, dev, max(max_rows, 1), plan())
         eng.zero_grads()
-        try:
-            for e in range(self.n_epochs):
-                if e + 1 < self.n_epochs:
-                    epoch_orders[e + 1] = order_provider()
-                    ready[e + 1].set()
-                losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
-                loss_ptr = losses.data_ptr()
-                for s, (b0, nb) in enumerate(bounds):
-                    Xs, Cs, m, slot = streamer.next()
-                    eng.fit_step(Xs, Cs, None, m, nb, self.lr, self.weight_decay, loss_ptr + 4 * s, world=world)
-                    streamer.release(slot)
-                host = losses.cpu()
-                self.loss_history.extend(host.unbind(0))
-        finally:
-            for ev in ready:
-                ev.set()
+        log = _LossLog(self.loss_history)
+        for e in range(self.n_epochs):
+            losses = torch.empty(len(bounds), dtype=torch.float32, device=dev)
+            loss_ptr = losses.data_ptr()
+            for s, (b0, nb) in enumerate(bounds):
+                Xs, Cs, m, slot = streamer.next()
+                eng.fit_step(Xs, Cs, None, m, nb, self.lr, self.weight_decay, loss_ptr + 4 * s, world=world)
+                streamer.release(slot)
+            log.push(losses)
+        log.flush()
         streamer.close()
         self.h2d_bytes_last_fit = streamer.bytes_h2d
         self.opt._publish_state(eng)

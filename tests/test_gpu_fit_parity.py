@@ -133,8 +133,15 @@ def test_c3_fit_through_the_api_matches_oracle_fit():
 def test_c3_fit_streamed_ingestion_is_the_same_trajectory():
     """ingest='stream' (rows of each step gathered on the host and uploaded one step ahead) must not change a bit of
     the batch composition: compare with the oracle like the resident mode."""
-    m = _fit_check(C3, 3000, 700, 2, seed=22, ingest="stream")
-    assert getattr(m, "h2d_bytes_last_fit", 0) == 2 * 3000 * 40 * 4
+    m = _fit_check(C3, 2000, 700, 4, seed=22, ingest="stream")       # 4 epochs: the two host order buffers are reused
+    assert getattr(m, "h2d_bytes_last_fit", 0) == 4 * 2000 * 40 * 4
+
+
+def test_readme_sized_fit_matches_oracle_fit_over_several_epochs():
+    """configs[0]-like flow (D=2, Cd=1, H=10, L=8), batches of 32 rows, 5 epochs: every step is one fused launch inside
+    rnvp_fit_epoch, losses are read back one epoch late, the epoch orders alternate between two host buffers."""
+    m = _fit_check((2, 1, 8, (10,)), 500, 32, 5, seed=25)
+    assert len(m.loss_history) == 5 * 16
 
 
 def test_c5_fit_through_the_api_matches_oracle_fit():

@@ -174,3 +174,69 @@ def test_device_shuffle_progressive_upload_trains_and_is_deterministic():
     ref = RealNVP(n_layers=4, hidden=(16,), lr=5e-3, n_epochs=3, batch_size=4096, shuffle='device', ingest='resident')
     ref.fit(X, Cn)
     assert abs(float(torch.stack(ref.loss_history)[-5:].mean()) - float(runs[0][-5:].mean())) < 0.3
+
+
+def test_fit_epoch_fused_step_equals_the_two_launch_step():
+    """README-sized batches (<= 32 rows) run as ONE launch per step inside rnvp_fit_epoch (fit kernel with the Adam update
+    fused behind it); the trajectory must equal the fit_step path (backward launch + Adam launch) bit for bit, and a
+    ragged last batch as well as a batch of more than 32 rows (two-launch fallback inside the same call) must work."""
+    dev = torch.device("cuda:0")
+    shape = (2, 1, 8, (10,))
+    n = 100                                                # 3 batches of 32 + one of 4
+    g = torch.Generator().manual_seed(0)
+    X, Cn = torch.randn(n, 2, generator=g).to(dev), torch.randn(n, 1, generator=g).to(dev)
+    perm = torch.randperm(n, generator=g).to(dev)
+    for bs in (32, 48):
+        nf_a, _ = _flow(shape, 11, dev)
+        nf_b, _ = _flow(shape, 11, dev)
+        ea, eb = nf_a._fused(), nf_b._fused()
+        steps = (n + bs - 1) // bs
+        la, lb = torch.zeros(steps, device=dev), torch.zeros(steps, device=dev)
+        ea.zero_grads(), eb.zero_grads()
+        for _ in range(2):                                 # two epochs: the Adam step counter carries over
+            ea.fit_epoch(X, Cn, perm, n, bs, 0.01, 0.0, la)
+            for s in range(steps):
+                nb = min(bs, n - s * bs)
+                eb.fit_step(X, Cn, perm[s * bs:s * bs + nb], nb, nb, 0.01, 0.0, lb[s:s + 1])
+        assert torch.equal(la, lb)
+        assert torch.equal(ea.flat, eb.flat) and torch.equal(ea.packed, eb.packed)
+        assert torch.equal(ea.exp_avg, eb.exp_avg) and torch.equal(ea.exp_avg_sq, eb.exp_avg_sq)
+        assert float(ea.gpacked.abs().max()) == 0.0 and ea.adam_steps == eb.adam_steps == 2 * steps
+
+
+def test_sample_result_lives_in_recycled_pinned_memory_and_equals_the_one_shot_path():
+    """Large sample() results are pipelined in row chunks into pinned memory lent by ingest.RESULTS: same values as one
+    launch over all rows (noise keyed on the global row index), views keep the buffer alive, dropping the array recycles it."""
+    import gc
+    from probaforms_b200.models import RealNVP
+    import probaforms_b200.ingest as I
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    m = RealNVP(n_layers=4, hidden=(64,), batch_size=4096, n_epochs=1, lr=1e-3)
+    torch.manual_seed(0)
+    m.fit(rng.standard_normal((8192, 32)), rng.standard_normal((8192, 8)))
+    eng = m.nf._fused()
+    n = 300_001
+    Cs = rng.standard_normal((n, 8)).astype(np.float32)
+    got = m.sample(Cs, seed=99)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == (n, 32)
+    assert type(got.base).__name__ == "_LentBuffer"
+    want = eng.sample(n, torch.from_numpy(Cs).to(dev), seed=99).cpu().numpy()
+    assert np.array_equal(got, want)
+    chunked = m._sample_to_host(eng, Cs, 0, n, [99], False, chunk_rows=70_000)     # ragged last chunk
+    assert np.array_equal(chunked, want)
+    many = m.sample(Cs[:50_000], n_draws=3, seed=5)
+    assert many.shape == (3, 50_000, 32)
+    for k in range(3):
+        assert np.array_equal(many[k], eng.sample(50_000, torch.from_numpy(Cs[:50_000]).to(dev), seed=5 + k).cpu().numpy())
+    view = got[1000:2000]
+    keep = view.copy()
+    free0 = len(I.RESULTS._free)
+    del got, chunked, many
+    gc.collect()
+    assert len(I.RESULTS._free) == free0 + 2                # `view` still pins the first buffer
+    again = m.sample(Cs, seed=123)                          # must not overwrite memory a live view points into
+    assert np.array_equal(view, keep)
+    del view, again
+    gc.collect()
+    assert len(I.RESULTS._free) >= free0 + 2

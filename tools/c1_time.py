@@ -15,21 +15,21 @@ for rep in range(3):
     hist = torch.stack(c1.loss_history)
     print("c1 fit: %.3f s, %.1f us/step, last-epoch mean loss %.4f" % (dt, dt / len(hist) * 1e6, float(hist[-32:].mean())))
 e1 = c1.nf._fused()
-Xs = torch.tensor(Xm[:32], dtype=torch.float32, device="cuda"); Cs1 = torch.tensor(ym[:32].reshape(-1, 1), dtype=torch.float32, device="cuda")
-l1 = torch.zeros(1, device="cuda")
+Xs = torch.tensor(Xm, dtype=torch.float32, device="cuda"); Cs1 = torch.tensor(ym.reshape(-1, 1), dtype=torch.float32, device="cuda")
+l1 = torch.zeros(32, device="cuda")
+perm = torch.randperm(1000, device="cuda")
 e1.zero_grads()
-for _ in range(20):
-    e1.fit_step(Xs, Cs1, None, 32, 32, 0.01, 0.0, l1)
+for _ in range(3):
+    e1.fit_epoch(Xs, Cs1, perm, 1000, 32, 0.01, 0.0, l1)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-for _ in range(200):
-    e1.fit_step(Xs, Cs1, None, 32, 32, 0.01, 0.0, l1)
+for _ in range(10):
+    e1.fit_epoch(Xs, Cs1, perm, 1000, 32, 0.01, 0.0, l1)
 b.record(); torch.cuda.synchronize()
-print("c1 fit_step (32 rows) GPU-timed loop: %.2f us/step" % (a.elapsed_time(b) / 200 * 1e3))
+print("c1 fit_epoch (fused steps) GPU-timed: %.2f us/step" % (a.elapsed_time(b) / 320 * 1e3))
 a.record()
 for _ in range(200):
-    e1.backward(Xs, Cs1, None, 32, -1.0 / 32)
+    e1.fit_step(Xs, Cs1, perm[:32], 32, 32, 0.01, 0.0, l1)
 b.record(); torch.cuda.synchronize()
-print("c1 backward only: %.2f us/launch" % (a.elapsed_time(b) / 200 * 1e3))
-e1.zero_grads()
+print("c1 fit_step (two launches) GPU-timed: %.2f us/step" % (a.elapsed_time(b) / 200 * 1e3))
