@@ -221,9 +221,12 @@ def rows_to_numpy(lib, t, chunk_bytes=32 << 20):
 
 class ChunkUploader:
     """Sequential, chunked upload of host rows into ONE resident device tensor while the consumer already works on the
-    chunks that have arrived: a helper thread converts chunk k+1 (float64 -> float32, or a plain copy) into one of two
-    pinned staging buffers while chunk k is on the bus; ``wait_rows(r)`` makes the current stream wait for the copies that
-    cover rows [0, r).  ``X`` / ``C`` are the device tensors (valid up to the rows waited for)."""
+    chunks that have arrived.  ``wait_rows(r)`` converts (float64 -> float32, or a plain copy; a pool of host threads,
+    non-temporal stores) and enqueues every chunk that covers rows [0, r) plus one chunk of look-ahead, through two
+    pinned staging buffers, and makes the current stream wait for those copies.  All of it happens on the CALLER's
+    thread: the consumer launches its kernels asynchronously, so the conversion of chunk k+1 runs while the GPU is busy
+    with chunk k (a helper thread driving the same CUDA context was measured slower, see StepStreamer).
+    ``X`` / ``C`` are the device tensors (valid up to the rows waited for)."""
 
     def __init__(self, lib, X, Cn, dev, chunk_rows):
         self.lib, self.dev = lib, dev
@@ -236,63 +239,51 @@ class ChunkUploader:
         self.stage = [(_pinned((self.chunk, w), ("cux", k)), _pinned((self.chunk, wc), ("cuc", k)) if wc else None) for k in range(2)]
         self.n_chunks = (n + self.chunk - 1) // self.chunk
         self.events = [None] * self.n_chunks
-        self._cv = threading.Condition()
-        self._err = None
-        self._waited = 0
+        self._next = 0                      # first chunk not yet enqueued
+        self._waited = 0                    # first chunk the consumer's stream has not been made to wait for
+        self.threads = host_threads()
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self._thread = threading.Thread(target=self._work, daemon=True)
-        self._thread.start()
 
-    def _work(self):
-        try:
-            torch.cuda.set_device(self.dev)
-            threads = host_threads()
-            done = [None, None]
-            for k in range(self.n_chunks):
-                r0 = k * self.chunk
-                m = min(self.chunk, self.n - r0)
-                sx, sc = self.stage[k & 1]
-                if done[k & 1] is not None:
-                    done[k & 1].synchronize()                        # the copy that last used this staging buffer has finished
-                rc = self.lib.rnvp_host_gather_xc(
-                    C.c_void_p(self.hX.ctypes.data), 1 if self.hX.dtype == np.float64 else 0, self.hX.shape[1],
-                    C.c_void_p(self.hC.ctypes.data) if self.hC is not None else None,
-                    1 if (self.hC is not None and self.hC.dtype == np.float64) else 0,
-                    self.hC.shape[1] if self.hC is not None else 0, None, r0, m,
-                    C.c_void_p(sx.data_ptr()), C.c_void_p(sc.data_ptr()) if sc is not None else None, threads)
-                if rc != 0:
-                    raise RuntimeError(f"rnvp_host_gather_xc failed (code {rc})")
-                with torch.cuda.stream(self.copy_stream):
-                    self.X[r0:r0 + m].copy_(sx[:m], non_blocking=True)
-                    if sc is not None:
-                        self.C[r0:r0 + m].copy_(sc[:m], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self.copy_stream)
-                done[k & 1] = ev
-                with self._cv:
-                    self.events[k] = ev
-                    self._cv.notify_all()
-        except BaseException as e:
-            with self._cv:
-                self._err = e
-                self._cv.notify_all()
+    def _enqueue(self, k):
+        r0 = k * self.chunk
+        m = min(self.chunk, self.n - r0)
+        sx, sc = self.stage[k & 1]
+        if k >= 2:
+            self.events[k - 2].synchronize()                        # the copy that last used this staging buffer has finished
+        rc = self.lib.rnvp_host_gather_xc(
+            C.c_void_p(self.hX.ctypes.data), 1 if self.hX.dtype == np.float64 else 0, self.hX.shape[1],
+            C.c_void_p(self.hC.ctypes.data) if self.hC is not None else None,
+            1 if (self.hC is not None and self.hC.dtype == np.float64) else 0,
+            self.hC.shape[1] if self.hC is not None else 0, None, r0, m,
+            C.c_void_p(sx.data_ptr()), C.c_void_p(sc.data_ptr()) if sc is not None else None, self.threads)
+        if rc != 0:
+            raise RuntimeError(f"rnvp_host_gather_xc failed (code {rc})")
+        with torch.cuda.stream(self.copy_stream):
+            self.X[r0:r0 + m].copy_(sx[:m], non_blocking=True)
+            if sc is not None:
+                self.C[r0:r0 + m].copy_(sc[:m], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.events[k] = ev
 
     def wait_rows(self, upto):
-        """The current stream waits until rows [0, upto) are resident (the host blocks only until their copies are enqueued)."""
+        """The current stream waits until rows [0, upto) are resident; one further chunk is converted and enqueued ahead."""
         last = (min(upto, self.n) + self.chunk - 1) // self.chunk
+        ahead = 0 if self._next == 0 else 1                        # the very first call only fetches what it needs
+        while self._next < min(self.n_chunks, last + ahead):
+            self._enqueue(self._next)
+            self._next += 1
         cur = torch.cuda.current_stream(self.dev)
         while self._waited < last:
-            with self._cv:
-                while self.events[self._waited] is None and self._err is None:
-                    self._cv.wait()
-                if self._err is not None:
-                    raise self._err
             cur.wait_event(self.events[self._waited])
             self._waited += 1
 
     def close(self):
-        self._thread.join()
+        """Upload whatever has not been asked for yet and wait for the staging buffers (shared by later calls)."""
         self.wait_rows(self.n)
+        for ev in self.events[-2:]:
+            if ev is not None:
+                ev.synchronize()
 
 
 class StepStreamer:
