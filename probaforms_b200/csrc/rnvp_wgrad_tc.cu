@@ -17,7 +17,7 @@
 //               separate TMEM accumulators
 //   warps 4-11  unit owners (two threads per TMEM lane = hidden unit, 16 of the stage's 32 rows each): dh^T from TMEM, h
 //               from the raw ring, delta1 = dh*act'(h), write delta1^T and h^T (hi/lo) back to TMEM as the A operands, db1
-//               in a register; every FOLD stages they drain the accumulators into fp32 register sums (the tensor core
+//               in a register; every WT_FOLD stages they drain the accumulators into fp32 register sums (the tensor core
 //               TRUNCATES when it accumulates, so chains are kept short -- tools/mma_rounding_probe.py) and at the end
 //               flush everything with red.global.add
 // Nets share a lane block through a block-diagonal trick: the W2^T image of a unit holds its own net's W2 column in its
@@ -42,7 +42,12 @@ constexpr int WT_THREADS = 416;             // warps 0-1 issuers, 2-3 converters
 constexpr int WT_KG = 36;                   // floats between K-groups (4 rows) of a K-major-over-rows tile: 144 B, so that the
                                             // transposing 4-byte stores of a warp (lanes = rows) hit 32 different banks
 constexpr int WT_NG = 8 * WT_KG;            // floats between 8-column groups (SBO = 1152 B)
-constexpr int WT_FOLD = 4;                  // stages per accumulator chain (16 accumulations of K = 8)
+#ifndef RNVP_WT_FOLD
+#define RNVP_WT_FOLD 8
+#endif
+constexpr int WT_FOLD = RNVP_WT_FOLD;       // stages per accumulator chain (32 accumulations of K = 8).  Measured on the c3 step
+                                            // (fit kernels, M rows/s | gradient error / max|grad|, bound 2e-5): 4: 68.4 | 3.5e-6,
+                                            // 8: 69.3 | 4.0e-6, 16: 69.9 | 4.4e-6 (c5 sweep vs fp64 4.3e-6 of its 5e-6 bound), 32: fails
 
 // Wait accounting (development aid, compile with -DRNVP_WG_TRACE; rnvp_debug_set_trace): when a trace buffer is set, every role of CTA 0 sums the cycles
 // it spends in each of its mbarrier waits and writes the totals at the end: trace[role * 8 + k] (role 0 issuer A, 1 issuer

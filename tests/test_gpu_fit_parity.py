@@ -57,6 +57,7 @@ def _grad_check(shape, N, n_res, seed, gather, expect_tc_fit):
     ref = torch.cat([grads_ref[k].reshape(-1) for k in O.param_order(L, len(hidden))])
     gmax = float(ref.abs().max())
     err = float((got - ref).abs().max())
+    print(f"gradient parity {shape} N={N}: max|err| / max|grad| = {err / gmax:.3e} (bound 2e-5)")
     assert err < 2e-5 * gmax, (err, gmax)
     assert torch.equal(got == 0, ref == 0) or int((got != 0).sum()) <= int((ref != 0).sum())   # masked entries: exact zeros
 
