@@ -129,10 +129,12 @@ int rnvp_adam_step(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_
 
 /* One epoch of the reference's fit loop (realnvp.py:238-254) as ONE call: for every consecutive slice of `batch_size`
  * entries of the epoch's row order d_perm[n] (the last partial batch is kept): rnvp_backward with scale = -1/nb, then
- * rnvp_adam_step (step count step0 + 1, step0 + 2, ...), the step's loss written to d_losses[s].  Same kernels and
- * arithmetic as the two calls it wraps; it only removes the host-side per-step overhead, which dominates README-sized
- * batches (32 rows: 2 launches of ~10 us against ~50 us of Python / ctypes).  Single GPU (no all-reduce between the two).
- * d_gpacked and *d_loss_slot must be zero on entry and are zero again on return. */
+ * rnvp_adam_step (step count step0 + 1, step0 + 2, ...), the step's loss written to d_losses[s].  Same arithmetic as the
+ * two calls it wraps, bit for bit; it removes the host-side per-step overhead, which dominates README-sized batches, and
+ * for small flows whose batch fits one 32-row tile (the reference's default batch_size) each step is ONE launch: the
+ * fit kernel applies the Adam update, refreshes d_packed and hands the loss off itself (the step's gradient is already in
+ * its shared memory; 16 us per step on B200 against 23 us for the two launches).  Single GPU (no all-reduce between the
+ * two).  d_gpacked and *d_loss_slot must be zero on entry and are zero again on return. */
 int rnvp_fit_epoch(const rnvp_desc* d, float* d_flat, float* d_packed, float* d_gpacked, float* d_exp_avg, float* d_exp_avg_sq,
                    const float* d_X, const float* d_C, const int64_t* d_perm, int64_t n, int64_t batch_size, double lr,
                    double beta1, double beta2, double eps, double weight_decay, int64_t step0, float* d_loss_slot,
@@ -170,7 +172,10 @@ void rnvp_perm_destroy(rnvp_perm* p);
  * dst[r][0..width) = (float) src[idx ? idx[r] : row0 + r][0..width) for r in [0, n): the rows of one optimisation step,
  * converted from the caller's float64 (src_is_f64 != 0) or float32 array -- torch.tensor(X, dtype=float32) of
  * realnvp.py:226-228 fused with the batch gather of realnvp.py:237 -- into a (pinned) staging buffer, on up to `threads`
- * host threads.  rnvp_host_copy is a multi-threaded memcpy (the .cpu().numpy() of realnvp.py:281 into a fresh array). */
+ * host threads.  The staging buffer is written with non-temporal stores when it is 16-byte aligned and width % 4 == 0:
+ * its next reader is the GPU's DMA engine, and an upload whose source lines are dirty in many cores' caches runs at a
+ * quarter of the bus rate.  rnvp_host_copy is a multi-threaded memcpy (the .cpu().numpy() of realnvp.py:281 into a
+ * fresh pageable array; RealNVP.sample uses it only beyond the pinned result pool's cap). */
 int rnvp_host_gather_rows(const void* src, int src_is_f64, int64_t width, const int64_t* idx, int64_t row0, int64_t n,
                           float* dst, int threads);
 /* X and C rows of one step in one pass over idx (src_c may be NULL) */

@@ -85,3 +85,80 @@ def test_permutation_prefetcher_falls_back_to_whole_tensor_for_huge_n():
     assert p.streaming
     q = PermutationPrefetcher(100, 1, lib=None)
     assert not q.streaming and q.next().shape == (100,)
+
+
+def test_streaming_permutation_inline_and_threaded_paths_equal_torch_randperm():
+    """Below 32,768 rows the epoch order is computed inline (no helper thread), above it streams from a thread; both are
+    torch.randperm(n, generator=manual_seed(seed)) bit for bit, and wait(k) never returns before entry k is final."""
+    from probaforms_b200 import _lib
+    from probaforms_b200.batching import StreamingPermutation
+    lib = _lib.load()
+    for n in (1, 2, 1000, 32768, 32769, 300_000):
+        sp = StreamingPermutation(lib, 12345, n, pin=False)
+        assert (sp._thread is None) == (n <= 32768)
+        head = sp.wait(min(n, 17))[:min(n, 17)].clone()
+        full = sp.full().clone()
+        ref = torch.randperm(n, generator=torch.Generator().manual_seed(12345))
+        assert torch.equal(full, ref) and torch.equal(head, ref[:min(n, 17)])
+
+
+def test_lent_result_buffers_return_to_the_pool_only_when_every_view_is_gone():
+    """ingest.ResultPool hands out memory that backs numpy results; the buffer must outlive every view of the array and be
+    reused afterwards (exercised here with an unpinned stand-in: no CUDA needed for the ownership logic)."""
+    import gc
+    import probaforms_b200.ingest as I
+
+    class HostPool(I.ResultPool):
+        def lend(self, shape):
+            numel = int(np.prod(shape))
+            with self._lock:
+                fit = [b for b in self._free if numel <= b.numel() <= 2 * numel]
+                buf = fit[0] if fit else None
+                if buf is not None:
+                    self._free = [b for b in self._free if b is not buf]
+            if buf is None:
+                buf = torch.empty(numel, dtype=torch.float32)
+            return np.asarray(I._LentBuffer(self, buf, shape)), buf[:numel]
+
+    pool = HostPool()
+    arr, flat = pool.lend((6, 4))
+    flat.copy_(torch.arange(24.0))
+    assert arr.shape == (6, 4) and arr.dtype == np.float32 and arr.flags.writeable and float(arr[5, 3]) == 23.0
+    ptr = flat.data_ptr()
+    view = arr[2:4]
+    sub = view[:, 1:3]
+    del arr, flat
+    gc.collect()
+    assert len(pool._free) == 0
+    del view
+    gc.collect()
+    assert len(pool._free) == 0 and float(sub[0, 0]) == 9.0          # `sub` still reads valid memory
+    del sub
+    gc.collect()
+    assert len(pool._free) == 1
+    again, flat2 = pool.lend((5, 4))                                   # 20 <= 24 <= 40: the same buffer is lent again
+    assert flat2.data_ptr() == ptr
+    # without CUDA the real pool declines and callers take the pageable path
+    if not torch.cuda.is_available():
+        assert I.RESULTS.lend((1024, 1024)) == (None, None)
+
+
+def test_host_rows_accepts_a_read_only_memmap_without_copying(tmp_path):
+    """Ranks of one node may share one host copy of the data (np.memmap): host_rows must hand the C ABI its pages as is."""
+    import probaforms_b200.ingest as I
+    from probaforms_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    path = tmp_path / "rows.f32"
+    src = np.random.default_rng(0).standard_normal((1000, 8)).astype(np.float32)
+    mm = np.memmap(path, dtype=np.float32, mode="w+", shape=src.shape)
+    mm[:] = src
+    mm.flush()
+    ro = np.memmap(path, dtype=np.float32, mode="r", shape=src.shape)
+    rows = I.host_rows(ro)
+    assert rows.ctypes.data == ro.ctypes.data and rows.dtype == np.float32
+    idx = np.random.default_rng(1).permutation(1000)[:300].astype(np.int64)
+    dst = torch.empty(300, 8)
+    assert lib.rnvp_host_gather_rows(C.c_void_p(rows.ctypes.data), 0, 8, C.c_void_p(idx.ctypes.data), 0, 300,
+                                     C.c_void_p(dst.data_ptr()), 3) == 0
+    assert np.array_equal(dst.numpy(), src[idx])
