@@ -47,8 +47,10 @@ WORKLOADS = {
     # 75,776 = 148 SMs x 2 pairs of 128-row tiles x 256 rows: every persistent CTA of the tcgen05 fit kernel gets exactly two
     # row-tile pairs per step (no tail wave; at 65,536 rows 108 of the 148 CTAs get 2 pairs, the other 40 one)
     "c3": (32, 8, 16, (128,), 75776, "configs[2]: fit, 32-D rows, 8-D condition, L=16, H=128"),
-    "c4": (64, 16, 24, (128,), 32768, "configs[3]: 64-D rows, 16-D condition, L=24, H=128 (H assumed)"),
-    "c5": (128, 32, 8, (512,), 16384, "configs[4]: 128-D rows, 32-D condition, L=8 (assumed), H=512"),
+    # rows per fit launch of c4 / c5: whole waves of 128-row tiles on 148 SMs (2 resp. 1 tile per SM); the log-prob / sample
+    # launches use 8 resp. 4 times as many rows
+    "c4": (64, 16, 24, (128,), 37888, "configs[3]: 64-D rows, 16-D condition, L=24, H=128 (H assumed)"),
+    "c5": (128, 32, 8, (512,), 18944, "configs[4]: 128-D rows, 32-D condition, L=8 (assumed), H=512"),
 }
 
 
