@@ -478,6 +478,12 @@ def main():
                                                "rnvp_tile_kernel<TR,2> (FP32-FMA fused forward+backward)")})
                     if engo.fit_on_tensor_cores:
                         e1["fit_executed_tf32_tflops"] = 3 * r_fit / world * fo_fit / 1e12
+                    # the whole optimisation step (forward + backward, gradient all-reduce at N > 1, fused Adam) on per_o rows per GPU
+                    loss_o = torch.zeros(1, device=dev)
+                    r_step, ms_step = time_pass(lambda: engo.fit_step(Xo, Co, None, per_o, per_o * world, 1e-4, 0.0, loss_o,
+                                                                      world=world), per_o, reps=3)
+                    engo.zero_grads()
+                    e1.update({"fit_step_rows_s": r_step, "fit_step_ms": ms_step})
                 ent[tag] = e1
             engo.set_path(0)
             if name == "c5":
