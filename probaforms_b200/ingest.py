@@ -18,6 +18,7 @@ fit step takes a millisecond those two copies are the wall-clock bound, so here
 torch is plumbing here (pinned memory, streams, events); the byte moving is the C ABI's
 ``rnvp_host_*`` entry points (include/rnvp.h).
 """
+import collections
 import ctypes as C
 import os
 import threading
@@ -104,11 +105,23 @@ class ResultPool:
     def __init__(self, cap_bytes=4 << 30):
         self.cap, self.total = int(cap_bytes), 0
         self._free = []                                     # pinned flat float32 tensors
+        self._returned = collections.deque()                # buffers handed back by finalisers, not yet in _free
         self._lock = threading.Lock()
 
     def _give_back(self, buf):
+        # called from __del__, i.e. possibly from inside the garbage collector while this very thread holds _lock in
+        # lend(): only an atomic deque append here, the list is touched under the lock alone
+        self._returned.append(buf)
+
+    def _drain(self):
+        while self._returned:
+            self._free.append(self._returned.popleft())
+
+    def free_buffers(self):
+        """Number of idle buffers (after collecting what finalisers have handed back)."""
         with self._lock:
-            self._free.append(buf)
+            self._drain()
+            return len(self._free)
 
     def lend(self, shape):
         """(numpy float32 array of ``shape`` on pinned memory, flat torch view of the same memory) or (None, None)."""
@@ -116,6 +129,7 @@ class ResultPool:
         if numel == 0 or not torch.cuda.is_available():
             return None, None
         with self._lock:
+            self._drain()
             fit = [b for b in self._free if numel <= b.numel() <= 2 * numel]
             buf = min(fit, key=lambda b: b.numel()) if fit else None
             if buf is not None:

@@ -231,12 +231,12 @@ def test_sample_result_lives_in_recycled_pinned_memory_and_equals_the_one_shot_p
         assert np.array_equal(many[k], eng.sample(50_000, torch.from_numpy(Cs[:50_000]).to(dev), seed=5 + k).cpu().numpy())
     view = got[1000:2000]
     keep = view.copy()
-    free0 = len(I.RESULTS._free)
+    free0 = I.RESULTS.free_buffers()
     del got, chunked, many
     gc.collect()
-    assert len(I.RESULTS._free) == free0 + 2                # `view` still pins the first buffer
+    assert I.RESULTS.free_buffers() == free0 + 2                # `view` still pins the first buffer
     again = m.sample(Cs, seed=123)                          # must not overwrite memory a live view points into
     assert np.array_equal(view, keep)
     del view, again
     gc.collect()
-    assert len(I.RESULTS._free) >= free0 + 2
+    assert I.RESULTS.free_buffers() >= free0 + 2

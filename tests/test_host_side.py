@@ -112,6 +112,7 @@ def test_lent_result_buffers_return_to_the_pool_only_when_every_view_is_gone():
         def lend(self, shape):
             numel = int(np.prod(shape))
             with self._lock:
+                self._drain()
                 fit = [b for b in self._free if numel <= b.numel() <= 2 * numel]
                 buf = fit[0] if fit else None
                 if buf is not None:
@@ -129,13 +130,13 @@ def test_lent_result_buffers_return_to_the_pool_only_when_every_view_is_gone():
     sub = view[:, 1:3]
     del arr, flat
     gc.collect()
-    assert len(pool._free) == 0
+    assert pool.free_buffers() == 0
     del view
     gc.collect()
-    assert len(pool._free) == 0 and float(sub[0, 0]) == 9.0          # `sub` still reads valid memory
+    assert pool.free_buffers() == 0 and float(sub[0, 0]) == 9.0          # `sub` still reads valid memory
     del sub
     gc.collect()
-    assert len(pool._free) == 1
+    assert pool.free_buffers() == 1
     again, flat2 = pool.lend((5, 4))                                   # 20 <= 24 <= 40: the same buffer is lent again
     assert flat2.data_ptr() == ptr
     # without CUDA the real pool declines and callers take the pageable path
