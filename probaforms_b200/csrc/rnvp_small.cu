@@ -37,28 +37,8 @@ __device__ __forceinline__ float act_f(float v) {
   return fmaxf(v, 0.0f);
 }
 
-// The same tanh with the reciprocal on the FMA pipe: integer-trick seed (5 % error) + three Newton steps (6 FMA) leave
-// 0.5 ulp, i.e. at least the accuracy of MUFU.RCP.  The log-prob / sample kernels are bound by the MUFU pipe (2 MUFU per tanh,
-// ncu: XU 87 %, issue slots 55 %), so NEWTON_ROWS of the RPT rows a thread owns take this route: one MUFU instead of two
-// for them, eight more issue slots -- the split that loads both resources about equally.
-template <int ACT>
-__device__ __forceinline__ float act_f_fma_rcp(float v) {
-  if (ACT == 1) {
-    const float d = ex2_approx(fminf(v * 2.8853900817779268f, 64.0f)) + 1.0f;     // clamp: d stays finite for the seed trick
-    float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
-#pragma unroll
-    for (int it = 0; it < 3; ++it) r = fmaf(r, fmaf(-d, r, 1.0f), r);
-    return fmaf(-2.0f, r, 1.0f);
-  }
-  return fmaxf(v, 0.0f);
-}
-
 constexpr int RPT = 4;          // rows per thread
 constexpr int THREADS = 256;
-#ifndef RNVP_NEWTON_ROWS
-#define RNVP_NEWTON_ROWS 2
-#endif
-constexpr int NEWTON_ROWS = RNVP_NEWTON_ROWS;
 
 // t and s of one coupling layer for RPT rows.  xk: conditioning half, c: condition.
 template <int NE, int NC, int ACT>
@@ -93,7 +73,7 @@ __device__ __forceinline__ void conditioner_pair(const float* __restrict__ wl, i
         for (int e = 0; e < NE; ++e) a = fmaf(rv[e], xk[r][e], a);
 #pragma unroll
         for (int k = 0; k < NC; ++k) a = fmaf(rv[NE + k], c[r][k], a);
-        const float h = r < RPT - NEWTON_ROWS ? act_f<ACT>(a) : act_f_fma_rcp<ACT>(a);
+        const float h = act_f<ACT>(a);
 #pragma unroll
         for (int e = 0; e < NE; ++e) acc[r][e] = fmaf(rv[NE + NC + 1 + e], h, acc[r][e]);
       }
