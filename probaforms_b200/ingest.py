@@ -28,10 +28,12 @@ import numpy as np
 import torch
 
 
-def host_threads():
-    """Host threads one process may use for gathers / copies: the box's cores shared by the local ranks."""
+def host_threads(reserve=1):
+    """Host threads one process may use for gathers / copies: the box's cores shared by the local ranks, minus ``reserve``
+    cores left to other busy threads of the process (the helper thread that shuffles the epoch order; 0 when there is none:
+    the calling thread takes part in the parallel region itself)."""
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return max(1, min(16, (os.cpu_count() or 1) // max(local_world, 1) - 1))
+    return max(1, min(16, (os.cpu_count() or 1) // max(local_world, 1) - int(reserve)))
 
 
 def host_rows(A):
@@ -255,7 +257,7 @@ class ChunkUploader:
         self.events = [None] * self.n_chunks
         self._next = 0                      # first chunk not yet enqueued
         self._waited = 0                    # first chunk the consumer's stream has not been made to wait for
-        self.threads = host_threads()
+        self.threads = host_threads(reserve=0)
         self.copy_stream = torch.cuda.Stream(device=dev)
 
     def _enqueue(self, k):
