@@ -352,7 +352,7 @@ class RealNVP(GenModel):
         """Fit on X [n, var_size] (numpy), optional conditions C [n, cond_size] (realnvp.py:210-262).
 
         Per step: loss = -nf.log_prob(batch); zero_grad; backward; Adam step -- executed as one fused
-        forward+backward launch plus one fused Adam launch.  ``loss_history`` gets one 0-d CPU tensor
+        forward+backward launch plus one fused Adam launch (README-sized batches: ONE launch per step).  ``loss_history`` gets one 0-d CPU tensor
         per step (as upstream); an epoch's losses are read back one epoch later (no per-epoch device synchronisation).
 
         Under an initialised ``torch.distributed`` group every rank passes the SAME X, C; each
@@ -361,8 +361,8 @@ class RealNVP(GenModel):
         single-process trajectory up to fp32 summation order.
 
         Ingestion (``ingest=`` constructor option): ``'resident'`` uploads the whole set once (chunked, conversion
-        fused) and gathers batches on the device; ``'stream'`` uploads, one step ahead of the kernels, only the rows
-        THIS rank needs for each step (host gather + conversion into pinned buffers on a helper thread);
+        fused) and gathers batches on the device; ``'stream'`` uploads, two steps ahead of the kernels, only the rows
+        THIS rank needs for each step (host gather + conversion into pinned buffers by a pool of host threads);
         ``'auto'`` streams when that moves fewer bytes (host data, n_epochs <= world size, large batches).
         """
         if not hasattr(X, "shape") or (C is not None and not hasattr(C, "shape")):
