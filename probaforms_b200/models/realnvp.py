@@ -628,8 +628,8 @@ class RealNVP(GenModel):
         host = flat.view(len(seeds), n, D)
         chunk = int(chunk_rows or max(65536, min(n, (64 << 20) // (4 * D))))
         chunk = max(1, min(chunk, n))
-        # the conditions go up chunk by chunk on a helper thread (conversion into pinned staging + H2D) while this thread
-        # already launches the kernels of the chunks that have arrived
+        # the conditions go up chunk by chunk (conversion into pinned staging + H2D, one chunk of look-ahead) while the GPU
+        # already runs the kernels of the chunks that have arrived
         on_dev = isinstance(Cs, torch.Tensor) and Cs.device.type != "cpu"
         C_dev = self._to_device(Cs, dev) if on_dev else None
         up = None if (Cs is None or on_dev) else ChunkUploader(eng.lib, Cs, None, dev, chunk)
