@@ -31,6 +31,11 @@
 
 namespace {
 using namespace tc05;
+#ifdef RNVP_SPLIT_RN
+#define SPLIT_A split_tf32
+#else
+#define SPLIT_A split_tf32_raw_hi          // A operands (TMEM): see tc05.cuh
+#endif
 
 constexpr int WD_THREADS = 320;       // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (TMEM lane quarter = warp % 4)
 constexpr int WD_STAGES = 4;          // weight ring depth (chunk steps in flight)
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
             float v = 0.0f;
             if (k < Cd && valid) v = __ldg(a.C + src * Cd + k);
             if (k == Cd) v = 1.0f;
-            split_tf32(v, hi[j], lo[j]);
+            split_tf32(v, hi[j], lo[j]);          // u (24-48 values per row-layer): the fully rounded split
           }
           tmem_st_x8(trow + U_HI + DH + e0, hi);
           tmem_st_x8(trow + U_LO + DH + e0, lo);
@@ -393,7 +398,7 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
                                                      __uint_as_float(r[4 * m + 2]), __uint_as_float(r[4 * m + 3])));
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_tf32(__uint_as_float(r[j]), r[j], lo[j]);
+            for (int j = 0; j < 16; ++j) SPLIT_A(__uint_as_float(r[j]), r[j], lo[j]);
             tmem_st_x16(d1, r);
             tmem_st_x16(d1 + CU, lo);
           }
@@ -530,8 +535,8 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
                   d2t[4 * m + q2] = gT[e];                                   // dL/dt
                   d2s[4 * m + q2] = fmaf(gT[e] * xs4[q2], es, gld);          // dL/ds = g_y * x * exp(s) + g_logdet
                   gT[e] *= es;                                               // dL/dx_T
-                  split_tf32(d2t[4 * m + q2], th[4 * m + q2], tl[4 * m + q2]);
-                  split_tf32(d2s[4 * m + q2], sh[4 * m + q2], sl[4 * m + q2]);
+                  SPLIT_A(d2t[4 * m + q2], th[4 * m + q2], tl[4 * m + q2]);
+                  SPLIT_A(d2s[4 * m + q2], sh[4 * m + q2], sl[4 * m + q2]);
                 }
               }
               tmem_st_x8(trow + E2H + half * HALF + e0, th);
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
               for (int j = 0; j < 16; ++j) {
                 const float h = __uint_as_float(hv[j]);
                 const float dp = ACT == 1 ? fmaf(-h, h, 1.0f) : (h > 0.0f ? 1.0f : 0.0f);
-                split_tf32(__uint_as_float(dh[j]) * dp, dh[j], lo[j]);
+                SPLIT_A(__uint_as_float(dh[j]) * dp, dh[j], lo[j]);
               }
               tmem_st_x16(d1, dh);
               tmem_st_x16(d1 + CU, lo);

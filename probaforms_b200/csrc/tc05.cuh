@@ -189,4 +189,13 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = round_tf32(v - __uint_as_float(hi));
 }
 
+// The same split for an A operand that goes to TMEM, in three instructions instead of five: the tensor core reads only the
+// upper 19 bits of an operand word, so hi is the RAW fp32 (effective value trunc(v), no instruction at all) and lo is
+// v - trunc(v) plus half a TF32 ulp (the hardware's truncation of lo then IS round-to-nearest).  |lo| < 2^-10 |v| instead of
+// <= 2^-11 |v|, so the residual error is 2^-22 |v| on average instead of 2^-23, still unbiased.
+__device__ __forceinline__ void split_tf32_raw_hi(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v);
+  lo = __float_as_uint(v - __uint_as_float(hi & 0xFFFFE000u)) + 0x1000u;
+}
+
 }  // namespace tc05
