@@ -128,10 +128,11 @@ __global__ void pack_kernel(const float* __restrict__ flat, float* __restrict__ 
 __global__ void pack_mma_kernel(const float* __restrict__ flat, float* __restrict__ img, const int* __restrict__ m2f, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const int m = m2f[i];
+    const int raw = m2f[i];
     float out = 0.0f;
-    if (m >= 0) {
-      const float v = flat[m >> 2];
+    if (raw >= 0) {
+      const int m = raw & ~RNVP_IMG_SCALED;
+      const float v = (raw & RNVP_IMG_SCALED) ? flat[m >> 2] * RNVP_TANH_PRESCALE : flat[m >> 2];
       const uint32_t h = (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u;          // round_tf32, see tc05.cuh
       const uint32_t l = (__float_as_uint(v - __uint_as_float(h)) + 0x1000u) & 0xFFFFE000u;
       const int code = m & 3;
@@ -185,10 +186,19 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ packe
     const int4 mm = reinterpret_cast<const int4*>(f2m)[i];
     const uint32_t h = (__float_as_uint(th) + 0x1000u) & 0xFFFFE000u;
     const float fh = __uint_as_float(h), fl = __uint_as_float((__float_as_uint(th - fh) + 0x1000u) & 0xFFFFE000u);
-    if (mm.x >= 0) mma_img[mm.x] = fh;
-    if (mm.y >= 0) mma_img[mm.y] = fl;
-    if (mm.z >= 0) mma_img[mm.z] = fh;
-    if (mm.w >= 0) mma_img[mm.w] = fl;
+    if ((mm.x >= 0 && (mm.x & RNVP_IMG_SCALED)) || (mm.y >= 0 && (mm.y & RNVP_IMG_SCALED))) {
+      // forward W1 image of a tanh flow: 2 log2(e) * theta (see build_mma_map)
+      const float ts = th * RNVP_TANH_PRESCALE;
+      const uint32_t hs = (__float_as_uint(ts) + 0x1000u) & 0xFFFFE000u;
+      const float fhs = __uint_as_float(hs), fls = __uint_as_float((__float_as_uint(ts - fhs) + 0x1000u) & 0xFFFFE000u);
+      if (mm.x >= 0) mma_img[mm.x & ~RNVP_IMG_SCALED] = fhs;
+      if (mm.y >= 0) mma_img[mm.y & ~RNVP_IMG_SCALED] = fls;
+    } else {
+      if (mm.x >= 0) mma_img[mm.x] = fh;
+      if (mm.y >= 0) mma_img[mm.y] = fl;
+    }
+    if (mm.z >= 0) mma_img[mm.z & ~RNVP_IMG_SCALED] = fh;
+    if (mm.w >= 0) mma_img[mm.w & ~RNVP_IMG_SCALED] = fl;
   }
 }
 
@@ -373,9 +383,10 @@ int rnvp_desc_create(int D, int Cd, int L, int n_hidden, const int* hidden, int 
     std::vector<int> f2m(4 * (size_t)d->P, -1);       // per parameter: hi, lo, hi (transposed image), lo (transposed image)
     for (size_t m = 0; m < m2f.size(); ++m)
       if (m2f[m] >= 0 && (m2f[m] & 3) < 2) {
-        int* slot = &f2m[4 * (size_t)(m2f[m] >> 2) + (m2f[m] & 3)];
+        const int v = m2f[m] & ~RNVP_IMG_SCALED;
+        int* slot = &f2m[4 * (size_t)(v >> 2) + (v & 3)];
         if (*slot >= 0) slot += 2;
-        *slot = (int)m;
+        *slot = (int)m | (m2f[m] & RNVP_IMG_SCALED);       // the slot remembers whether its image holds the pre-scaled value
       }
     e = cudaMalloc(&d->d_m2f, sizeof(int) * m2f.size());
     if (e == cudaSuccess) e = cudaMemcpy(d->d_m2f, m2f.data(), sizeof(int) * m2f.size(), cudaMemcpyHostToDevice);

@@ -157,7 +157,12 @@ inline void build_layout(FlowGeom* d) {
 // (8 rows x 16 B core matrices, 128 B each, K-adjacent core matrices contiguous): see tc05.cuh
 inline int mma_tiled_off(int n, int k, int K) { return (n >> 3) * (K >> 2) * 32 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
 
-// map of the tcgen05 region: value = 4*flat_index + code (0: TF32 hi image, 1: lo remainder, 2: full fp32), or -1 (zero)
+// map of the tcgen05 region: value = 4*flat_index + code (0: TF32 hi image, 1: lo remainder, 2: full fp32), or -1 (zero).
+// RNVP_IMG_SCALED (bit 30) marks the entries of the FORWARD W1 image (weights and the b1 column) of a tanh flow: they hold
+// 2*log2(e) times the parameter, so that GEMM1 delivers the argument of the tanh's ex2 directly and the epilogue saves one
+// multiply per hidden activation.  Nothing else reads that image (the backward products use the transposed images).
+constexpr int RNVP_IMG_SCALED = 1 << 30;
+constexpr float RNVP_TANH_PRESCALE = 2.8853900817779268f;       // tanh(a) = 1 - 2 / (2^(a * 2 log2 e) + 1)
 inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
   m2f.assign(d->mma_ok ? d->mma_floats : 0, -1);
   if (!d->mma_ok) return;
@@ -182,7 +187,7 @@ inline void build_mma_map(const FlowGeom* d, std::vector<int>& m2f) {
             if (k < DH) { const int xk = lg.par == 0 ? 2 * k + 1 : 2 * k; if (xk < D) f = g0.flat_w[net] + (int64_t)unit * (D + Cd) + xk; }
             else if (k < DH + Cd) f = g0.flat_w[net] + (int64_t)unit * (D + Cd) + D + (k - DH);
             else if (k == DH + Cd) f = g0.flat_b[net] + unit;
-            if (f >= 0) m2f[blk + mma_tiled_off(n, k, K1P)] = (int)(4 * f + part);
+            if (f >= 0) m2f[blk + mma_tiled_off(n, k, K1P)] = (int)(4 * f + part) | (d->act == 1 ? RNVP_IMG_SCALED : 0);
           }
         }
       }

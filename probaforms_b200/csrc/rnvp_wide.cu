@@ -44,7 +44,7 @@ template <int ACT>
 __device__ __forceinline__ float act_wide(float v) {
   if (ACT == 1) {
     float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 2.8853900817779268f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v));        // v = 2 log2(e) * pre-activation: the W1 image is pre-scaled (rnvp_planner.h)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
     return fmaf(-2.0f, r, 1.0f);
   }
