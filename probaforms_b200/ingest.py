@@ -28,12 +28,15 @@ import numpy as np
 import torch
 
 
-def host_threads(reserve=1):
-    """Host threads one process may use for gathers / copies: the box's cores shared by the local ranks, minus ``reserve``
-    cores left to other busy threads of the process (the helper thread that shuffles the epoch order; 0 when there is none:
-    the calling thread takes part in the parallel region itself)."""
+def host_threads(reserve=1, use_both_of_two=True):
+    """Host threads one process may use for gathers / copies (the calling thread is one of them): the box's cores shared by
+    the local ranks, minus ``reserve`` cores left to whatever else is runnable (the helper thread that shuffles the epoch
+    order, the CUDA driver's threads) -- a parallel region that owns every core waits a whole time slice whenever one of its
+    workers is descheduled.  A rank that owns only two cores still uses both (8 ranks on a 16-core host) unless the caller
+    runs a busy helper thread of its own beside the region (``use_both_of_two=False``: the streamed reference shuffle)."""
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return max(1, min(16, (os.cpu_count() or 1) // max(local_world, 1) - int(reserve)))
+    cores = (os.cpu_count() or 1) // max(local_world, 1)
+    return max(1, min(cores, 2) if use_both_of_two else 1, min(16, cores - int(reserve)))
 
 
 def host_rows(A):
@@ -257,7 +260,7 @@ class ChunkUploader:
         self.events = [None] * self.n_chunks
         self._next = 0                      # first chunk not yet enqueued
         self._waited = 0                    # first chunk the consumer's stream has not been made to wait for
-        self.threads = host_threads(reserve=0)
+        self.threads = host_threads()
         self.copy_stream = torch.cuda.Stream(device=dev)
 
     def _enqueue(self, k):
@@ -327,7 +330,7 @@ class StepStreamer:
         self.free = [(k, None) for k in range(self.SLOTS)]      # FIFO of (slot, event: the step that used it has run)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.bytes_h2d = 0
-        self.threads = host_threads()
+        self.threads = host_threads(use_both_of_two=False)     # the epoch order is being shuffled on a helper thread
         self._plan = iter(plan)
         self.trace = [] if os.environ.get("RNVP_INGEST_TRACE") else None    # (slot wait, order wait, gather, enqueue) seconds per step
         self.trace_events = []                                              # (upload start, upload end) CUDA events per step
