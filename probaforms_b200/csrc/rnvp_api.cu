@@ -32,6 +32,7 @@ cudaError_t rnvp_launch_mma(int DH, int act, int mode, const RnvpMmaArgs& a, int
 size_t rnvp_mma_smem_bytes(int w1_floats, int w2_floats, int w1t_floats);
 cudaError_t rnvp_launch_wgrad_tc(int NU, int TP, const RnvpWgradTcArgs& a, int grid, cudaStream_t st);
 cudaError_t rnvp_launch_wide(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, cudaStream_t st);
+int rnvp_wide_ctas_per_sm(int DH);
 cudaError_t rnvp_launch_mma_selftest(const float* A, const float* B, float* D, int N, int K, int passes, cudaStream_t st);
 
 namespace {
@@ -311,7 +312,7 @@ int run_mma(rnvp_desc* d, int mode, int l0, int l1, const float* packed, const f
     if (tiles > 0x7fffffffLL) return fail(RNVP_EINVAL, "too many rows for one launch");
     a.n_pairs = (int)tiles;                      // rnvp_wide.cu walks single 128-row tiles
     if (records) { a.rec = wgrad_rec_floats(d); a.Npad = fit_npad(d, N); }
-    const long long ctas = (long long)d->num_sms * (d->mDH == 16 ? 2 : 1);       // D = 32 flows: two CTAs per SM
+    const long long ctas = (long long)d->num_sms * rnvp_wide_ctas_per_sm(d->mDH);   // DH <= 32: two CTAs per SM
     cudaError_t e = rnvp_launch_wide(d->mDH, d->act, mode, a, (int)std::min<long long>(tiles, ctas), stream);
     if (e != cudaSuccess) return cuda_fail(e, "tcgen05 streamed kernel launch");
     return 0;

@@ -69,18 +69,25 @@ __device__ __forceinline__ void tmem_ld_w(uint32_t taddr, uint32_t (&r)[W]) {
 // barrier indices: ring full / empty first, then the tile hand-offs
 enum { WB_WF = 0, WB_WE = WD_STAGES, WB_UF = 2 * WD_STAGES, WB_D1F0, WB_D1F1, WB_AF0, WB_AF1, WB_D2F, WB_XF, WB_XE, WB_COUNT };
 
+// DH <= 32: two CTAs per SM (256 TMEM columns each).  DH = 16 keeps the double-buffered D1 / dh chunk ring; DH = 32 only fits
+// with ONE ring buffer (forward 240, backward 256 columns): the GEMM1 of the next chunk step is then issued behind this
+// step's GEMM2 instead of ahead of it, and the second CTA on the SM fills the gap.
+#ifndef RNVP_WIDE32_CTAS
+#define RNVP_WIDE32_CTAS 2
+#endif
 template <int DH, int CDMAX, int CU, int ACT, int MODE>
-__global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel(const __grid_constant__ RnvpMmaArgs a) {
+__global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : (DH == 32 ? RNVP_WIDE32_CTAS : 1)) rnvp_wide_kernel(const __grid_constant__ RnvpMmaArgs a) {
   constexpr int K1PMAX = (DH + CDMAX + 1 + 7) & ~7;
   constexpr int NTP = (DH + 15) & ~15;
+  constexpr int NB1 = (DH == 32 && RNVP_WIDE32_CTAS == 2) ? 1 : 2;      // buffers of the D1 (forward) / dh (backward) chunk ring
   constexpr int HALF = DH / 2;                         // features of each parity class owned by one thread of a row pair
   // TMEM columns
   constexpr int U_HI = 0, U_LO = K1PMAX, D1B = 2 * K1PMAX;               // D1 ring: buffer b at D1B + b*2*CU: [D1/A_hi | A_lo]
-  constexpr int D2C = D1B + 4 * CU, C2C = D2C + NTP, TCOLS = C2C + NTP;
+  constexpr int D2C = D1B + 2 * NB1 * CU, C2C = D2C + NTP, TCOLS = C2C + NTP;
   static_assert(TCOLS <= 512, "TMEM budget");
   static_assert(DH % 16 == 0 && (K1PMAX - DH) % 8 == 0 && CU == 32, "layout assumptions");
   // backward sweep (MODE 2): delta2 hi / lo (2 DH columns each), the dh / delta1 chunk ring, the du accumulators [main | corr]
-  constexpr int E2H = 0, E2L = 2 * DH, DHB = 4 * DH, DUM = DHB + 4 * CU, DUC = DUM + NTP;
+  constexpr int E2H = 0, E2L = 2 * DH, DHB = 4 * DH, DUM = DHB + 2 * NB1 * CU, DUC = DUM + NTP;
   static_assert(DUC + NTP <= 512, "TMEM budget (backward)");
   // D = 32 flows need 224 columns in either sweep: two CTAs share an SM (256 columns each, 80 registers per thread)
   constexpr int TALLOC = (TCOLS <= 256 && DUC + NTP <= 256) ? 256 : 512;
@@ -227,14 +234,16 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
           __syncwarp();
         }
         for (int cc = 0; cc < NCS; ++cc, ++step) {
-          const int st = (int)(step % WD_STAGES), buf = cc & 1;
-          if (cc + 1 < NCS) {                 // next chunk's GEMM1 first: the tensor core stays busy during this chunk's epilogue
-            const int st1 = (int)((step + 1) % WD_STAGES);
+          const int st = (int)(step % WD_STAGES), buf = cc & (NB1 - 1);
+          auto next_gemm1 = [&]() {           // GEMM1 of chunk step cc + 1 into the other (NB1 = 2) or the same (NB1 = 1) buffer
+            const int st1 = (int)((step + 1) % WD_STAGES), nb = (cc + 1) & (NB1 - 1);
             mbar_wait(&bars[WB_WF + st1], (ph_w >> st1) & 1u); ph_w ^= 1u << st1;
             fence_after_sync();
-            if (leader) { gemm1(st1, buf ^ 1); mma_commit(&bars[WB_D1F0 + (buf ^ 1)]); }
+            if (leader) { gemm1(st1, nb); mma_commit(&bars[WB_D1F0 + nb]); }
             __syncwarp();
-          }
+          };
+          // two buffers: the next chunk's GEMM1 first, the tensor core stays busy during this chunk's epilogue
+          if (NB1 == 2 && cc + 1 < NCS) next_gemm1();
           mbar_wait(&bars[WB_AF0 + buf], (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
           fence_after_sync();
           if (leader) {
@@ -244,6 +253,8 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
             if (cc + 1 == NC || cc + 1 == NCS) mma_commit(&bars[WB_D2F]);
           }
           __syncwarp();
+          // one buffer: the next GEMM1 overwrites the A operand this GEMM2 reads -- issued behind it (MMAs execute in order)
+          if (NB1 == 1 && cc + 1 < NCS) next_gemm1();
         }
       }
       if (do_bwd) {
@@ -257,14 +268,15 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
             __syncwarp();
           }
           for (int cc = 0; cc < NCS; ++cc, ++step) {
-            const int st = (int)(step % WD_STAGES), buf = cc & 1;
-            if (cc + 1 < NCS) {
-              const int st1 = (int)((step + 1) % WD_STAGES);
+            const int st = (int)(step % WD_STAGES), buf = cc & (NB1 - 1);
+            auto next_gemmA = [&]() {
+              const int st1 = (int)((step + 1) % WD_STAGES), nb = (cc + 1) & (NB1 - 1);
               mbar_wait(&bars[WB_WF + st1], (ph_w >> st1) & 1u); ph_w ^= 1u << st1;
               fence_after_sync();
-              if (leader) { gemmA(st1, buf ^ 1, (cc + 1) >= NC ? 1 : 0); mma_commit(&bars[WB_D1F0 + (buf ^ 1)]); }
+              if (leader) { gemmA(st1, nb, (cc + 1) >= NC ? 1 : 0); mma_commit(&bars[WB_D1F0 + nb]); }
               __syncwarp();
-            }
+            };
+            if (NB1 == 2 && cc + 1 < NCS) next_gemmA();
             mbar_wait(&bars[WB_AF0 + buf], (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
             fence_after_sync();
             if (leader) {
@@ -273,6 +285,7 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
               if (cc + 1 == NCS) mma_commit(&bars[WB_D2F]);       // du of the layer complete
             }
             __syncwarp();
+            if (NB1 == 1 && cc + 1 < NCS) next_gemmA();
           }
         }
       }
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
         }
         float tpark[HALF];
         for (int cc = 0; cc < NCS; ++cc) {
-          const int buf = cc & 1;
+          const int buf = cc & (NB1 - 1);
           mbar_wait(&bars[WB_D1F0 + buf], (ph_d1 >> buf) & 1u); ph_d1 ^= 1u << buf;
           fence_after_sync();
           {
@@ -553,7 +566,7 @@ __global__ void __launch_bounds__(WD_THREADS, DH == 16 ? 2 : 1) rnvp_wide_kernel
             mbar_arrive(&bars[WB_UF]);
             // ---- chunk steps: delta1 = dh * act'(h), dh from the tensor core, h from the record the forward sweep wrote
             for (int cc = 0; cc < NCS; ++cc) {
-              const int buf = cc & 1, net = cc >= NC ? 1 : 0;
+              const int buf = cc & (NB1 - 1), net = cc >= NC ? 1 : 0;
               const int col0 = net * H + (cc - net * NC) * CU + 16 * half;
               uint32_t hv[16];
 #pragma unroll
@@ -636,6 +649,8 @@ size_t rnvp_wide_smem_bytes(int DH, int CDMAX) {
   const size_t stage = ((size_t)(2 * CU * K1PMAX + 2 * NTP * CU + 2 * NTP * 8) + 31) & ~(size_t)31;
   return WD_STAGES * stage * 4 + 8 * WB_COUNT + 256 * 4 + 64;
 }
+
+int rnvp_wide_ctas_per_sm(int DH) { return DH == 16 ? 2 : (DH == 32 ? RNVP_WIDE32_CTAS : 1); }
 
 cudaError_t rnvp_launch_wide(int DH, int act, int mode, const RnvpMmaArgs& a, int grid, cudaStream_t st) {
   if (DH == 64) return launch_wide_shape<64, 32>(act, mode, a, grid, rnvp_wide_smem_bytes(64, 32), st);
