@@ -521,18 +521,22 @@ def main():
                 warm.fit(Xm, ym.reshape(-1, 1))
                 warm.sample(ym.reshape(-1, 1))
                 torch.cuda.synchronize()
-                torch.manual_seed(0)                                    # cold start, as the README runs it
-                mm = RealNVP(lr=0.01, n_epochs=100)
-                t0 = time.perf_counter()
-                mm.fit(Xm, ym.reshape(-1, 1))
-                torch.cuda.synchronize()
-                dt = time.perf_counter() - t0
+                walls = []
+                for _rep in range(3):                                   # three cold starts (fresh model, seed 0): the median is
+                    torch.manual_seed(0)                                # reported, all three are listed (host jitter: 0.07-0.3 s)
+                    mm = RealNVP(lr=0.01, n_epochs=100)
+                    t0 = time.perf_counter()
+                    mm.fit(Xm, ym.reshape(-1, 1))
+                    torch.cuda.synchronize()
+                    walls.append(time.perf_counter() - t0)
+                dt = sorted(walls)[1]
                 t0 = time.perf_counter()
                 Sm = mm.sample(ym.reshape(-1, 1))
                 ds = time.perf_counter() - t0
                 hist = [float(v) for v in mm.loss_history]
                 last_epoch = sum(hist[-32:]) / 32
                 c1 = {"fit_wall_s": dt, "steps": len(hist), "rows_per_s": 100000 / dt, "us_per_step": dt / max(len(hist), 1) * 1e6,
+                      "fit_wall_s_all": walls,
                       "final_loss": hist[-1], "last_epoch_mean_loss": last_epoch, "sample_1000_rows_ms": ds * 1e3,
                       "sample_shape": list(Sm.shape),
                       "note": "cold-start torch.manual_seed(0) fit through the public API (one launch per 32-row step: fit kernel with the Adam update fused behind it)"}
