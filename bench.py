@@ -30,6 +30,7 @@ also       configs[0] (c1, with the reference CPU path run in full beside it), [
            rows per GPU = 1 B rows on 8 GPUs) and [4] (c5: tensor-core path and FP32-FMA path side by side).
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -524,6 +525,9 @@ def main():
                 walls = []
                 for _rep in range(3):                                   # three cold starts (fresh model, seed 0): the median is
                     torch.manual_seed(0)                                # reported, all three are listed (host jitter: 0.07-0.3 s)
+                    mm = None
+                    gc.collect()                                        # the previous model's descriptor / buffers die here, not
+                    torch.cuda.synchronize()                            # inside the next timed region
                     mm = RealNVP(lr=0.01, n_epochs=100)
                     t0 = time.perf_counter()
                     mm.fit(Xm, ym.reshape(-1, 1))
