@@ -163,3 +163,15 @@ def test_host_rows_accepts_a_read_only_memmap_without_copying(tmp_path):
     assert lib.rnvp_host_gather_rows(C.c_void_p(rows.ctypes.data), 0, 8, C.c_void_p(idx.ctypes.data), 0, 300,
                                      C.c_void_p(dst.data_ptr()), 3) == 0
     assert np.array_equal(dst.numpy(), src[idx])
+
+
+def test_host_thread_budget_per_rank(monkeypatch):
+    """Cores are shared by the local ranks; one is left to stray threads, a two-core rank uses both unless the caller runs a
+    busy helper thread beside the parallel region."""
+    import probaforms_b200.ingest as I
+    cases = [(1, 16, 15, 15), (2, 16, 7, 7), (4, 16, 3, 3), (8, 16, 2, 1), (8, 8, 1, 1), (1, 1, 1, 1), (1, 2, 2, 1), (1, 64, 16, 16)]
+    for local_world, cpus, want, want_helper in cases:
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", str(local_world))
+        monkeypatch.setattr(I.os, "cpu_count", lambda c=cpus: c)
+        assert I.host_threads() == want, (local_world, cpus)
+        assert I.host_threads(use_both_of_two=False) == want_helper, (local_world, cpus)
