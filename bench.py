@@ -472,9 +472,9 @@ def main():
                     e1.update({"fit_kernel_rows_s": r_fit, "fit_rows_per_launch": per_o, "fit_ms": ms_fit,
                                "fit_algorithmic_tflops": r_fit / world * fo_fit / 1e12,
                                "fit_kernels": ("rnvp_wide_kernel<64,32,32,1,2> (tcgen05 streamed forward + backward sweeps) + "
-                                               "rnvp_wgrad_tc_kernel<96,96,64,..,single-net> (tcgen05 weight-gradient sweep)"
+                                               "rnvp_wgrad_tc_kernel<96,64,1,2,2,true> (tcgen05 weight-gradient sweep, single-net lane blocks)"
                                                if engo.fit_on_tensor_cores and name == "c5" else
-                                               "rnvp_wide_kernel<32,16,32,1,2> + rnvp_wgrad_tc_kernel<48,48,32,..> (tcgen05)"
+                                               "rnvp_wide_kernel<32,16,32,1,2> (two CTAs per SM) + rnvp_wgrad_tc_kernel<48,32,1,2,3,false> (tcgen05)"
                                                if engo.fit_on_tensor_cores else
                                                "rnvp_tile_kernel<TR,2> (FP32-FMA fused forward+backward)")})
                     if engo.fit_on_tensor_cores:
